@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py -- MSDeformAttn forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload, BASELINE.json configs[1]): the multi-scale deformable attention of the
+GroundingDINO SwinT-OGC 6-layer deformable encoder at 800x1333, batch 4 per GPU, bf16 value with fp32
+sampling locations / attention weights, forward + backward.  One STEP = the 6 layers' op forward
+(layer 0..5) then the 6 layers' op backward (layer 5..0), each layer on its own tensors (3.3 GB in
+total, so nothing survives in the 126 MB L2 between uses).  Inputs are what a randomly initialised
+model feeds the op (distribution "I"): value ~ N(0,1), reference points at the
+pixel centres, offsets from the default-initialised sampling_offsets bias, uniform attention weights.
+
+metric/value : algorithmic bytes of the step (every input read once, every output
+               written once) / device time, summed over GPUs.  Inputs resident in HBM.
+e2e          : the same work through the host-buffer C-ABI entry (msda_host_fwd_bwd): pinned host
+               inputs -> H2D -> forward -> backward -> D2H of all four results, per layer call.
+roofline     : the backward scatter kernel (dominant), bracketed by CUDA events inside the timed steps.
+cpu_baseline : the reference's CPU path (grid_sample formulation, oracle/torch_port.py) on this host.
+--impl reference : that CPU path alone, same metric/unit/config, bounded sample per step.
+
+N > 1 (torchrun): every rank runs the same per-GPU workload (the path shards by batch with no data-path
+collective -- "replicas only"); time = max over ranks, value = N x per-GPU bytes / time.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "open-groundingdino_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+SWIN_T_800x1333 = [(100, 167), (50, 84), (25, 42), (13, 21)]
+METRIC = "msda_fwd_bwd_algorithmic_hbm_throughput"
+UNIT = "GB/s"
+
+CONFIGS = {
+    # name: (shapes, batch, Lq (None = one query per pixel), value dtype, layers)
+    "cfg2": dict(shapes=SWIN_T_800x1333, N=4, Lq=None, dtype="bf16", layers=6,
+                 text="SwinT-OGC 800x1333 6-layer deformable-encoder MSDeformAttn fwd+bwd, bs=4/GPU, bf16 value + fp32 loc/attn"),
+    "cfg1": dict(shapes=SWIN_T_800x1333, N=1, Lq=None, dtype="f32", layers=6,
+                 text="SwinT-OGC 800x1333 encoder MSDeformAttn fwd+bwd, bs=1, fp32 (6 independent layers per step)"),
+    "cfg3": dict(shapes=SWIN_T_800x1333, N=8, Lq=900, dtype="f32", layers=6,
+                 text="SwinT-OGC decoder cross-attention MSDeformAttn fwd+bwd, 900 queries, bs=8, fp32, 6 layers"),
+}
+M, D, P = 8, 32, 4
+
+
+def algorithmic_bytes(N, S, L, Lq, e_v, e_l=4):
+    fwd = N * (S * M * D * e_v + Lq * M * L * P * 3 * e_l + Lq * M * D * e_v)
+    bwd = N * (2 * S * M * D * e_v + Lq * M * D * e_v + 2 * Lq * M * L * P * 3 * e_l)
+    return fwd, bwd
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, torch_device_index):
+        self.samples, self.mask, self.max_mhz, self.ok = [], 0, None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as exc:  # pragma: no cover
+            self.err = repr(exc)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": [name for bit, name in self.REASONS.items() if self.mask & bit]}
+
+
+# --------------------------------------------------------------------------------------------------
+def make_layer_inputs(torch, cfg, dist, seed, device):
+    """One layer's op inputs, generated on the device (distribution "I" or "U")."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    shapes = cfg["shapes"]
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    N = cfg["N"]
+    Lq = cfg["Lq"] or S
+    vdt = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
+    value = torch.randn(N, S, M, D, generator=g, device=device).to(vdt)
+    grad_out = torch.randn(N, Lq, M * D, generator=g, device=device).to(vdt)
+    sh = torch.tensor(shapes, dtype=torch.long, device=device)
+    st = torch.cat((sh.new_zeros(1), sh.prod(1).cumsum(0)[:-1]))
+    if dist == "U":
+        loc = torch.rand(N, Lq, M, L, P, 2, generator=g, device=device)
+        attn = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, device=device), -1).view(N, Lq, M, L, P)
+    else:
+        import math
+        if Lq == S:     # encoder: pixel centres of the query's own level (transformer.py:470-485, valid_ratio 1)
+            pts = []
+            for h, w in shapes:
+                ys = (torch.arange(h, device=device, dtype=torch.float32) + 0.5) / h
+                xs = (torch.arange(w, device=device, dtype=torch.float32) + 0.5) / w
+                yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+                pts.append(torch.stack([xx.reshape(-1), yy.reshape(-1)], -1))
+            ref = torch.cat(pts, 0)[None].expand(N, -1, -1)
+        else:           # decoder: sigmoid(N(0,1)) centres
+            ref = torch.sigmoid(torch.randn(N, Lq, 2, generator=g, device=device))
+        ang = torch.arange(M, dtype=torch.float32, device=device) * (2.0 * math.pi / M)
+        d = torch.stack([ang.cos(), ang.sin()], -1)
+        d = d / d.abs().max(-1, keepdim=True)[0]
+        off = d[:, None, None, :] * torch.arange(1, P + 1, device=device, dtype=torch.float32)[None, None, :, None]
+        off = off.expand(M, L, P, 2)
+        wh = torch.stack([sh[:, 1], sh[:, 0]], -1).float()
+        loc = (ref[:, :, None, None, None, :] + (off / wh[None, :, None, :])[None, None]).contiguous()
+        attn = torch.full((N, Lq, M, L, P), 1.0 / (L * P), device=device)
+    return dict(value=value, loc=loc.contiguous(), attn=attn.contiguous(), grad_out=grad_out, shapes=sh, starts=st,
+                dims=(N, S, M, D, L, Lq, P))
+
+
+class OurLayer:
+    """Pre-allocated buffers + raw C-ABI calls for one layer (no allocation inside the timed region)."""
+
+    def __init__(self, torch, lib_mod, inp, variant):
+        self.torch, self.L = torch, lib_mod
+        self.lib = lib_mod.lib()
+        self.i = inp
+        N, S, M_, D_, L, Lq, P_ = inp["dims"]
+        v = inp["value"]
+        self.code = lib_mod.MSDA_BF16 if v.dtype == torch.bfloat16 else lib_mod.MSDA_F32
+        self.out = torch.empty(N, Lq, M_ * D_, dtype=v.dtype, device=v.device)
+        self.gv = torch.empty_like(v)
+        self.gl = torch.empty_like(inp["loc"])
+        self.ga = torch.empty_like(inp["attn"])
+        self.ws_bytes = self.lib.msda_backward_workspace_bytes(N, S, M_, D_, L, Lq, P_, self.code, 0)
+        self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=v.device)
+        self.acc = self.ws if self.code == lib_mod.MSDA_BF16 else self.gv
+        self.variant = variant
+        self.n_value = v.numel()
+
+    def forward(self):
+        i = self.i
+        rc = self.lib.msda_forward(i["value"].data_ptr(), i["shapes"].data_ptr(), i["starts"].data_ptr(),
+                                   i["loc"].data_ptr(), i["attn"].data_ptr(), self.out.data_ptr(), *i["dims"],
+                                   self.code, self.variant, self.torch.cuda.current_stream().cuda_stream)
+        self.L.check(rc, "msda_forward")
+
+    def backward(self, ev0=None, ev1=None):
+        """zero accumulator | scatter kernel (bracketed by ev0/ev1) | bf16 narrowing -- the same three
+        stages msda_backward(variant=0) enqueues, split with the NO_ZERO/NO_NARROW bits."""
+        i, L = self.i, self.L
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.acc.zero_()
+        if ev0 is not None:
+            ev0.record()
+        rc = self.lib.msda_backward(i["value"].data_ptr(), i["shapes"].data_ptr(), i["starts"].data_ptr(),
+                                    i["loc"].data_ptr(), i["attn"].data_ptr(), i["grad_out"].data_ptr(),
+                                    self.gv.data_ptr(), self.gl.data_ptr(), self.ga.data_ptr(), *i["dims"], self.code, 0,
+                                    self.variant | L.VARIANT_NO_ZERO | L.VARIANT_NO_NARROW,
+                                    self.ws.data_ptr(), self.ws_bytes, stream)
+        L.check(rc, "msda_backward")
+        if ev1 is not None:
+            ev1.record()
+        if self.code == L.MSDA_BF16:
+            L.check(self.lib.msda_narrow_bf16(self.ws.data_ptr(), self.gv.data_ptr(), self.n_value, stream), "narrow")
+
+
+def cpu_reference_step(torch, cfg, threads, seed=1234):
+    """Bounded sample of the workload on the host cores: ONE image of ONE layer, fp32, fwd+bwd through the
+    grid_sample formulation the reference executes on CPU.  Returns a closure and its description."""
+    from oracle import torch_port
+    torch.set_num_threads(threads)
+    sub = dict(cfg, N=1, dtype="f32")
+    inp = make_layer_inputs(torch, sub, "I", seed, "cpu")
+    shapes = [tuple(x) for x in cfg["shapes"]]
+
+    def step():
+        torch_port.fwd_bwd(inp["value"], shapes, inp["loc"], inp["attn"], inp["grad_out"])
+
+    return step, "1 image of 1 layer (1/%d of a step), fp32 on CPU, grid_sample path, fwd+bwd" % (cfg["N"] * cfg["layers"])
+
+
+def sample_bytes(cfg):
+    """Algorithmic bytes of the CPU sample, counted with the WORKLOAD's storage types so that GB/s ratios
+    between arms are time ratios for equal work."""
+    S = sum(h * w for h, w in cfg["shapes"])
+    e_v = 2 if cfg["dtype"] == "bf16" else 4
+    f, b = algorithmic_bytes(1, S, len(cfg["shapes"]), cfg["Lq"] or S, e_v)
+    return f + b
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    step, desc = cpu_reference_step(torch, cfg, threads)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    gbs = sample_bytes(cfg) / dt / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["text"], "sample_per_step": desc},
+            "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+            "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from msda_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    layers = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, args.dist, 100 + l, device), args.variant)
+              for l in range(cfg["layers"])]
+    nl = len(layers)
+
+    def step(events=None):
+        for lay in layers:
+            lay.forward()
+        for k, lay in enumerate(reversed(layers)):
+            if events is None:
+                lay.backward()
+            else:
+                lay.backward(events[k][0], events[k][1])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    bwd_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
+                  for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for k in range(args.steps):
+            step(bwd_events[k])
+        e1.record()
+        barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    bwd_kernel_ms = sum(a.elapsed_time(b) for evs in bwd_events for a, b in evs) / (args.steps * nl)
+
+    # forward kernel alone (outside the timed region, same buffers)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(3):
+        for lay in layers:
+            lay.forward()
+    f1.record()
+    torch.cuda.synchronize()
+    fwd_kernel_ms = f0.elapsed_time(f1) / (3 * nl)
+
+    N, S, _, _, L, Lq, _ = layers[0].i["dims"]
+    e_v = 2 if cfg["dtype"] == "bf16" else 4
+    b_fwd, b_bwd = algorithmic_bytes(N, S, L, Lq, e_v)
+    step_bytes = (b_fwd + b_bwd) * nl
+    value = world * step_bytes / (ms_step * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+    bwd_gbs = b_bwd / (bwd_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "bwd_kernel_dram_bytes.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "bwd_vec_kernel (grad_value scatter + grad_loc/grad_attn)",
+                "achieved": bwd_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bwd_gbs / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": b_bwd, "kernel_ms": bwd_kernel_ms,
+                "fwd_kernel": {"achieved": b_fwd / (fwd_kernel_ms * 1e-3) / 1e9, "kernel_ms": fwd_kernel_ms,
+                               "frac": b_fwd / (fwd_kernel_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b_fwd},
+                "step_frac": (step_bytes / (ms_step * 1e-3) / 1e9) / peak}
+
+    # ---- end to end through the host-buffer C ABI ------------------------------------------------
+    lib = _lib.lib()
+    ctx = ctypes.c_void_p()
+    code = layers[0].code
+    _lib.check(lib.msda_host_create(ctypes.byref(ctx), N, S, M, D, L, Lq, P, code, 0), "msda_host_create")
+    i0 = layers[0].i
+    pin = lambda t: t.detach().cpu().pin_memory()
+    h_in = {k: pin(i0[k]) for k in ("value", "shapes", "starts", "loc", "attn", "grad_out")}
+    h_out = {"out": torch.empty_like(h_in["grad_out"]).pin_memory(), "gv": torch.empty_like(h_in["value"]).pin_memory(),
+             "gl": torch.empty_like(h_in["loc"]).pin_memory(), "ga": torch.empty_like(h_in["attn"]).pin_memory()}
+
+    def e2e_step():
+        for _ in range(nl):
+            rc = lib.msda_host_fwd_bwd(ctx, h_in["value"].data_ptr(), h_in["shapes"].data_ptr(), h_in["starts"].data_ptr(),
+                                       h_in["loc"].data_ptr(), h_in["attn"].data_ptr(), h_in["grad_out"].data_ptr(),
+                                       h_out["out"].data_ptr(), h_out["gv"].data_ptr(), h_out["gl"].data_ptr(),
+                                       h_out["ga"].data_ptr())
+            _lib.check(rc, "msda_host_fwd_bwd")
+
+    e2e_steps = min(args.steps, args.e2e_steps)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    e2e = {"value": world * step_bytes / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_bytes_per_step": int(lib.msda_host_h2d_bytes(ctx)) * nl,
+           "d2h_bytes_per_step": int(lib.msda_host_d2h_bytes(ctx)) * nl,
+           "api": "msda_host_fwd_bwd (include/msda_b200.h), pinned host buffers, one call per layer"}
+    lib.msda_host_destroy(ctx)
+
+    extra = {}
+    if rank == 0 and not args.no_ref_cuda:
+        extra["reference_cuda_op"] = time_reference_cuda(torch, layers, cfg, ms_step)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cstep, desc = cpu_reference_step(torch, cfg, threads)
+        for _ in range(2):
+            cstep()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 5 or (time.perf_counter() - t0 < 10.0 and reps < 40):
+            cstep()
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": sample_bytes(cfg) / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": desc + f"; {reps} reps, {dt * 1e3:.0f} ms each", "ms_per_sample": dt * 1e3}
+
+    if rank == 0:
+        launches_per_step = nl * (1 + 1 + (1 if code == _lib.MSDA_BF16 else 0))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if cfg["dtype"] == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": cfg["text"], "config_id": args.config, "distribution": args.dist, "layers": nl,
+                           "batch_per_gpu": N, "value_tokens": S, "queries": Lq, "heads": M, "channels_per_head": D,
+                           "levels": L, "points": P, "coord_dtype": "f32", "accumulate_dtype": "f32",
+                           "backward_mode": "atomic", "variant": args.variant, "parallelism": f"replicas x{world}",
+                           "l2_policy": "inputs larger than L2 (each layer has its own %.0f MB of tensors)" % (step_bytes / nl / 1e6),
+                           "algorithmic_bytes_per_step": step_bytes},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks.summary(), "ms_fwd_per_layer": fwd_kernel_ms, "ms_bwd_kernel_per_layer": bwd_kernel_ms}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_reference_cuda(torch, layers, cfg, ours_ms_step):
+    """The reference's own CUDA op (oracle/_ref, fp32 only) on the same tensors, same step structure.  For a
+    bf16 workload it is wrapped exactly like the reference wraps fp16 (ops/modules/ms_deform_attn.py:114-120):
+    widen value/grad to fp32, run, narrow the result; the casts are inside its time."""
+    try:
+        from oracle import ref_cuda
+        ref = ref_cuda.load()
+    except Exception as exc:
+        return {"unavailable": repr(exc)[:120]}
+    if ref is None:
+        return {"unavailable": "oracle/_ref/msda_ref_cuda.so not built"}
+    bf16 = cfg["dtype"] == "bf16"
+
+    def step():
+        for lay in layers:
+            i = lay.i
+            v = i["value"].float() if bf16 else i["value"]
+            o = ref.ms_deform_attn_forward(v, i["shapes"], i["starts"], i["loc"], i["attn"], 64)
+            if bf16:
+                o = o.to(torch.bfloat16)
+        for lay in reversed(layers):
+            i = lay.i
+            v = i["value"].float() if bf16 else i["value"]
+            g = i["grad_out"].float() if bf16 else i["grad_out"]
+            gv, gl, ga = ref.ms_deform_attn_backward(v, i["shapes"], i["starts"], i["loc"], i["attn"], g, 64)
+            if bf16:
+                gv = gv.to(torch.bfloat16)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    return {"ms_per_step": ms, "speedup_ours": ms / ours_ms_step, "note": "same GPU, same tensors, fp32 op" + (" + casts" if bf16 else "")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--dist", default="I", choices=["I", "U"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

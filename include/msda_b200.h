@@ -1,0 +1,125 @@
+/*
+ * msda_b200.h -- C ABI of libmsda_b200.so: multi-scale deformable attention for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function the reference exposes
+ * through its pybind module `MultiScaleDeformableAttention` (paths relative to
+ * /root/reference/models/GroundingDINO/ops/):
+ *
+ *   msda_forward            <- ms_deform_attn_forward   src/ms_deform_attn.h:20-39,  src/vision.cpp:14
+ *                              (= ms_deform_attn_cuda_forward  src/cuda/ms_deform_attn_cuda.cu:20-80)
+ *   msda_backward           <- ms_deform_attn_backward  src/ms_deform_attn.h:41-61,  src/vision.cpp:15
+ *                              (= ms_deform_attn_cuda_backward src/cuda/ms_deform_attn_cuda.cu:83-153)
+ *   msda_backward_workspace_bytes  (new: the reference allocates inside the op; here the caller owns
+ *                              every byte, so the library never allocates and holds no state)
+ *   msda_sample_index       (new, test hook: the integer side of the sampler,
+ *                              src/cuda/ms_deform_im2col_cuda.cuh:285-288,38-41,274-278, for the
+ *                              bit-exactness tests)
+ *   msda_host_*             (new: the same forward+backward driven from HOST buffers, used for the
+ *                              end-to-end measurement and by non-torch callers)
+ *
+ * Conventions
+ *   - plain pointers and ints only; no torch / ATen types; device pointers unless the name says host
+ *   - tensors are contiguous, row-major, exactly the reference layouts:
+ *       value             (N, S, M, D)          dtype = value_dtype
+ *       spatial_shapes    (L, 2) int64, (H, W)  device memory, read by the kernels (no host sync)
+ *       level_start_index (L)    int64          device memory
+ *       sampling_loc      (N, Lq, M, L, P, 2)   (x, y) normalised to [0,1]; fp32 (fp64 for MSDA_F64)
+ *       attn_weight       (N, Lq, M, L, P)      fp32 (fp64 for MSDA_F64)
+ *       output            (N, Lq, M*D)          dtype = value_dtype
+ *       grad_output/grad_value like output/value; grad_sampling_loc/grad_attn_weight like their inputs
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it
+ *   - return value: 0 on success, a negative MSDA_E_* code for a rejected call, or a positive
+ *     cudaError_t if the CUDA runtime reported one.  Nothing is thrown, printed or swallowed.
+ *   - im2col_step (reference .cu:50-52) does not appear: results never depended on it; the Python
+ *     mirror keeps the argument and its `batch % step == 0` check.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* dtype of value / output / grad_output / grad_value */
+enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2 };
+
+/* backward accumulation mode for grad_value */
+enum {
+  MSDA_BWD_ATOMIC = 0,        /* vector red.global.add into fp32 (order not reproducible)        */
+  MSDA_BWD_DETERMINISTIC = 1  /* two-pass: bucket samples by destination, then ordered gather-sum */
+};
+
+enum {
+  MSDA_OK = 0,
+  MSDA_E_INVALID = -1,      /* null pointer, non-positive dimension, bad enum                       */
+  MSDA_E_UNSUPPORTED = -2,  /* combination this build has no kernel for                            */
+  MSDA_E_WORKSPACE = -3,    /* workspace missing or smaller than msda_backward_workspace_bytes()   */
+  MSDA_E_TOO_LARGE = -4     /* a per-batch slab exceeds 32-bit element indexing                    */
+};
+
+int msda_abi_version(void);
+const char *msda_error_string(int code);
+
+/* Variant selector for experiments and A/B profiling; 0 = the library's default choice.
+ * bit 0..3  : kernel family (1 = generic per-channel kernels, 2 = vector kernels, linear order,
+ *             3 = vector kernels, query-tile order)
+ * bit 8      : (backward, atomic mode) MSDA_VARIANT_NO_ZERO   -- the caller has already zeroed the
+ *             accumulator (grad_value, or the workspace for bf16); skip the memset
+ * bit 9      : (backward, bf16)         MSDA_VARIANT_NO_NARROW -- leave the fp32 accumulator in the
+ *             workspace and do not write grad_value; finish with msda_narrow_bf16()
+ *             (bits 8/9 let a profiler bracket the scatter kernel alone; same kernels, same order)
+ * other bits: reserved, must be 0. */
+#define MSDA_VARIANT_NO_ZERO 0x100
+#define MSDA_VARIANT_NO_NARROW 0x200
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output,
+                 int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                 int num_query, int num_point, int value_dtype, int variant, void *stream);
+
+size_t msda_backward_workspace_bytes(int batch, int spatial_size, int num_heads, int channels,
+                                     int num_levels, int num_query, int num_point, int value_dtype,
+                                     int mode);
+
+/* grad_value, grad_sampling_loc and grad_attn_weight are fully overwritten (no pre-zeroing needed). */
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                  int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                  int num_query, int num_point, int value_dtype, int mode, int variant,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* fp32 -> bf16 (round to nearest even) of n elements; the last stage of a bf16 backward. */
+int msda_narrow_bf16(const float *src, void *dst, size_t n, void *stream);
+
+/* rec: int32 (N, Lq, M, L, P, 4) = [h_low, w_low, flags, slab_row]; flags bit0 = sample accepted,
+ * bits1..4 = which of the 4 neighbours exist; slab_row = b*S + level_start_index[l].  fp32 path. */
+int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *sampling_loc, int batch, int spatial_size, int num_heads,
+                      int num_levels, int num_query, int num_point, int32_t *rec, void *stream);
+
+/* ---- host-buffer path ---------------------------------------------------------------------- */
+typedef struct msda_host_ctx msda_host_ctx;
+
+/* Allocates device buffers (and nothing else) for one problem size. */
+int msda_host_create(msda_host_ctx **ctx, int batch, int spatial_size, int num_heads, int channels,
+                     int num_levels, int num_query, int num_point, int value_dtype, int mode);
+void msda_host_destroy(msda_host_ctx *ctx);
+/* bytes moved per msda_host_fwd_bwd call */
+size_t msda_host_h2d_bytes(const msda_host_ctx *ctx);
+size_t msda_host_d2h_bytes(const msda_host_ctx *ctx);
+/* All pointers are HOST memory (pinned for full speed).  Copies inputs to the device, runs forward
+ * and backward, copies the four results back, and returns after the stream has drained. */
+int msda_host_fwd_bwd(msda_host_ctx *ctx, const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, const void *grad_output, void *output,
+                      void *grad_value, void *grad_sampling_loc, void *grad_attn_weight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

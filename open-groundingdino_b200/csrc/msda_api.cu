@@ -1,0 +1,256 @@
+// msda_api.cu -- the extern "C" surface declared in include/msda_b200.h: argument checks, kernel
+// family selection, accumulator handling, and the host-buffer path.  No allocation and no state
+// outside msda_host_ctx; every device call is enqueued on the caller's stream.
+#include <cstdlib>
+#include <new>
+
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+using namespace msda;
+
+namespace {
+
+struct DeviceInfo {
+  int sms = 0;
+};
+
+int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  return sms;
+}
+
+size_t elem_size(int dtype) { return dtype == MSDA_F64 ? 8 : dtype == MSDA_BF16 ? 2 : 4; }
+size_t coord_size(int dtype) { return dtype == MSDA_F64 ? 8 : 4; }
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_dims(int N, int S, int M, int D, int L, int Lq, int P, int dtype) {
+  if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0) return MSDA_E_INVALID;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F64) return MSDA_E_INVALID;
+  // in-slab offsets are 32-bit element indices (like the reference, cuh:47-53)
+  if ((long long)S * M * D >= (1LL << 31)) return MSDA_E_TOO_LARGE;
+  if ((long long)N * Lq * M * L * P * 2 >= (1LL << 40)) return MSDA_E_TOO_LARGE;
+  return MSDA_OK;
+}
+
+// family: 1 generic, 2 vector/linear order, 3 vector/query-tile order, 0 auto
+int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool all_aligned) {
+  const int want = variant & 15;
+  const bool vec_ok = fwd_vec_supported(dtype, D, P, L) && all_aligned;
+  if (want == 1 || !vec_ok) return 1;
+  if (want == 2) return 2;
+  if (want == 3) return 3;
+  return (Lq == S) ? 3 : 2;
+}
+
+int vec_grid(const Problem &pr) {
+  // Persistent CTAs: 2 x 256 threads fit per SM at <=128 registers; 4 waves' worth of CTAs keeps
+  // the grid-stride tail short without a host read of the (device-resident) shape table.
+  const long long items = (long long)pr.N * pr.Lq * pr.M;
+  const long long upper = (items + kUnitItems - 1) / kUnitItems + (long long)pr.N * pr.M * 4 * pr.L + 64;
+  const long long want = (long long)sm_count() * 8;
+  return (int)(upper < want ? upper : want);
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char *msda_error_string(int code) {
+  switch (code) {
+    case MSDA_OK: return "ok";
+    case MSDA_E_INVALID: return "invalid argument (null pointer, non-positive dimension or bad enum)";
+    case MSDA_E_UNSUPPORTED: return "unsupported dtype/shape/mode combination";
+    case MSDA_E_WORKSPACE: return "workspace missing or too small";
+    case MSDA_E_TOO_LARGE: return "tensor too large for 32-bit in-slab indexing";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown msda error";
+  }
+}
+
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output, int N, int S, int M, int D,
+                 int L, int Lq, int P, int dtype, int variant, void *stream_) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
+    return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Problem pr{};
+  pr.value = value; pr.shapes = spatial_shapes; pr.starts = level_start_index;
+  pr.loc = sampling_loc; pr.attn = attn_weight; pr.out = output;
+  pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.tile_w_log2 = 3;
+  const bool al = aligned16(value) && aligned16(sampling_loc) && aligned16(attn_weight) && aligned16(output);
+  const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
+  if (family == 1) return launch_forward_generic(pr, dtype, stream);
+  pr.tiled = (family == 3);
+  return launch_forward_vec(pr, dtype, vec_grid(pr), stream);
+}
+
+size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
+  if (check_dims(N, S, M, D, L, Lq, P, dtype) != MSDA_OK) return 0;
+  size_t bytes = 0;
+  if (dtype == MSDA_BF16) bytes += (size_t)N * S * M * D * sizeof(float);   // fp32 accumulator
+  if (mode == MSDA_BWD_DETERMINISTIC) bytes += deterministic_workspace_bytes(N, S, M, D, L, Lq, P, dtype);
+  return bytes;
+}
+
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
+                  void *grad_sampling_loc, void *grad_attn_weight, int N, int S, int M, int D, int L, int Lq,
+                  int P, int dtype, int mode, int variant, void *workspace, size_t workspace_bytes,
+                  void *stream_) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
+      !grad_value || !grad_sampling_loc || !grad_attn_weight)
+    return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (mode != MSDA_BWD_ATOMIC && mode != MSDA_BWD_DETERMINISTIC) return MSDA_E_INVALID;
+  const size_t need = msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dtype, mode);
+  if (need > 0 && (!workspace || workspace_bytes < need)) return MSDA_E_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  Problem pr{};
+  pr.value = value; pr.shapes = spatial_shapes; pr.starts = level_start_index;
+  pr.loc = sampling_loc; pr.attn = attn_weight; pr.grad_out = grad_output;
+  pr.grad_loc = grad_sampling_loc; pr.grad_attn = grad_attn_weight;
+  pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.tile_w_log2 = 3;
+
+  const size_t n_value = (size_t)N * S * M * D;
+  if (mode == MSDA_BWD_DETERMINISTIC) {
+    pr.grad_value_acc = grad_value;
+    return launch_backward_deterministic(pr, dtype, workspace, workspace_bytes, stream);
+  }
+
+  // atomic mode: accumulate into fp32 (fp64) -- grad_value itself, or the workspace for bf16
+  void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
+  const size_t acc_bytes = n_value * (dtype == MSDA_F64 ? 8 : 4);
+  if (!(variant & MSDA_VARIANT_NO_ZERO))
+    if (cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, stream)) return (int)e;
+  pr.grad_value_acc = acc;
+
+  const bool al = aligned16(value) && aligned16(sampling_loc) && aligned16(attn_weight) &&
+                  aligned16(grad_output) && aligned16(acc) && aligned16(grad_sampling_loc) &&
+                  aligned16(grad_attn_weight);
+  const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
+  int rc;
+  if (family == 1) {
+    rc = launch_backward_generic(pr, dtype, stream);
+  } else {
+    pr.tiled = (family == 3);
+    rc = launch_backward_vec(pr, dtype, vec_grid(pr), stream);
+  }
+  if (rc != MSDA_OK) return rc;
+  if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW)) rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, stream);
+  return rc;
+}
+
+int msda_narrow_bf16(const float *src, void *dst, size_t n, void *stream_) {
+  if (!src || !dst) return MSDA_E_INVALID;
+  if (n == 0) return MSDA_OK;
+  if (!aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return MSDA_E_INVALID;
+  return launch_f32_to_bf16(src, dst, (long long)n, static_cast<cudaStream_t>(stream_));
+}
+
+int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index, const float *sampling_loc,
+                      int N, int S, int M, int L, int Lq, int P, int32_t *rec, void *stream_) {
+  if (!spatial_shapes || !level_start_index || !sampling_loc || !rec) return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, 1, L, Lq, P, MSDA_F32)) return rc;
+  if (!aligned16(rec)) return MSDA_E_INVALID;
+  Problem pr{};
+  pr.shapes = spatial_shapes; pr.starts = level_start_index; pr.loc = sampling_loc;
+  pr.N = N; pr.S = S; pr.M = M; pr.D = 1; pr.L = L; pr.Lq = Lq; pr.P = P;
+  return launch_sample_index(pr, rec, static_cast<cudaStream_t>(stream_));
+}
+
+// ---- host-buffer path ---------------------------------------------------------------------------
+struct msda_host_ctx {
+  int N, S, M, D, L, Lq, P, dtype, mode;
+  size_t b_value, b_loc, b_attn, b_out, b_shapes, b_starts, b_ws;
+  char *d_value, *d_loc, *d_attn, *d_gout, *d_out, *d_gvalue, *d_gloc, *d_gattn, *d_ws;
+  int64_t *d_shapes, *d_starts;
+  cudaStream_t stream;
+};
+
+void msda_host_destroy(msda_host_ctx *c) {
+  if (!c) return;
+  void *ptrs[] = {c->d_value, c->d_loc, c->d_attn, c->d_gout, c->d_out, c->d_gvalue,
+                  c->d_gloc, c->d_gattn, c->d_ws, c->d_shapes, c->d_starts};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int msda_host_create(msda_host_ctx **out, int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
+  if (!out) return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  msda_host_ctx *c = new (std::nothrow) msda_host_ctx();
+  if (!c) return (int)cudaErrorMemoryAllocation;
+  c->N = N; c->S = S; c->M = M; c->D = D; c->L = L; c->Lq = Lq; c->P = P; c->dtype = dtype; c->mode = mode;
+  c->b_value = (size_t)N * S * M * D * elem_size(dtype);
+  c->b_out = (size_t)N * Lq * M * D * elem_size(dtype);
+  c->b_loc = (size_t)N * Lq * M * L * P * 2 * coord_size(dtype);
+  c->b_attn = c->b_loc / 2;
+  c->b_shapes = (size_t)L * 2 * sizeof(int64_t);
+  c->b_starts = (size_t)L * sizeof(int64_t);
+  c->b_ws = msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dtype, mode);
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  auto alloc = [&](char **p, size_t bytes) {
+    if (e == cudaSuccess && bytes > 0) e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
+  };
+  alloc(&c->d_value, c->b_value); alloc(&c->d_loc, c->b_loc); alloc(&c->d_attn, c->b_attn);
+  alloc(&c->d_gout, c->b_out); alloc(&c->d_out, c->b_out); alloc(&c->d_gvalue, c->b_value);
+  alloc(&c->d_gloc, c->b_loc); alloc(&c->d_gattn, c->b_attn); alloc(&c->d_ws, c->b_ws);
+  alloc(reinterpret_cast<char **>(&c->d_shapes), c->b_shapes);
+  alloc(reinterpret_cast<char **>(&c->d_starts), c->b_starts);
+  if (e != cudaSuccess) {
+    msda_host_destroy(c);
+    return (int)e;
+  }
+  *out = c;
+  return MSDA_OK;
+}
+
+size_t msda_host_h2d_bytes(const msda_host_ctx *c) {
+  return c ? c->b_value + c->b_loc + c->b_attn + c->b_out + c->b_shapes + c->b_starts : 0;
+}
+size_t msda_host_d2h_bytes(const msda_host_ctx *c) { return c ? c->b_out + c->b_value + c->b_loc + c->b_attn : 0; }
+
+int msda_host_fwd_bwd(msda_host_ctx *c, const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                      const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                      void *grad_attn_weight) {
+  if (!c || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
+      !output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
+    return MSDA_E_INVALID;
+  cudaStream_t s = c->stream;
+  cudaError_t e;
+#define MSDA_TRY(x) if ((e = (x)) != cudaSuccess) return (int)e
+  MSDA_TRY(cudaMemcpyAsync(c->d_shapes, spatial_shapes, c->b_shapes, cudaMemcpyHostToDevice, s));
+  MSDA_TRY(cudaMemcpyAsync(c->d_starts, level_start_index, c->b_starts, cudaMemcpyHostToDevice, s));
+  MSDA_TRY(cudaMemcpyAsync(c->d_value, value, c->b_value, cudaMemcpyHostToDevice, s));
+  MSDA_TRY(cudaMemcpyAsync(c->d_loc, sampling_loc, c->b_loc, cudaMemcpyHostToDevice, s));
+  MSDA_TRY(cudaMemcpyAsync(c->d_attn, attn_weight, c->b_attn, cudaMemcpyHostToDevice, s));
+  MSDA_TRY(cudaMemcpyAsync(c->d_gout, grad_output, c->b_out, cudaMemcpyHostToDevice, s));
+  int rc = msda_forward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_out, c->N, c->S, c->M,
+                        c->D, c->L, c->Lq, c->P, c->dtype, 0, s);
+  if (rc != MSDA_OK) return rc;
+  MSDA_TRY(cudaMemcpyAsync(output, c->d_out, c->b_out, cudaMemcpyDeviceToHost, s));
+  rc = msda_backward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_gout, c->d_gvalue,
+                     c->d_gloc, c->d_gattn, c->N, c->S, c->M, c->D, c->L, c->Lq, c->P, c->dtype, c->mode, 0,
+                     c->d_ws, c->b_ws, s);
+  if (rc != MSDA_OK) return rc;
+  MSDA_TRY(cudaMemcpyAsync(grad_value, c->d_gvalue, c->b_value, cudaMemcpyDeviceToHost, s));
+  MSDA_TRY(cudaMemcpyAsync(grad_sampling_loc, c->d_gloc, c->b_loc, cudaMemcpyDeviceToHost, s));
+  MSDA_TRY(cudaMemcpyAsync(grad_attn_weight, c->d_gattn, c->b_attn, cudaMemcpyDeviceToHost, s));
+  MSDA_TRY(cudaStreamSynchronize(s));
+#undef MSDA_TRY
+  return MSDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// msda_fwd.cu -- forward gather kernels (replaces ms_deformable_im2col_gpu_kernel,
+// reference ms_deform_im2col_cuda.cuh:237-299, and its launcher :923-954).
+//
+// Mapping.  A (query, head) "item" owns D output channels.  A lane owns 16 bytes of them (4 fp32 or
+// 8 bf16), so LPG = D*sizeof(VT)/16 lanes cover one head and one warp instruction gathers 32/LPG
+// whole 128-byte (fp32) or 64-byte (bf16) head rows.  The groups of a warp are spread over the
+// pyramid levels of an item: each group preloads the P (x,y) pairs and P attention weights of its
+// level with two or three 16-byte loads, computes the bilinear geometry in registers and issues the
+// 4*P corner gathers back to back; the per-level partial sums are combined with xor-shuffles and one
+// lane group stores the 16-byte chunks of the output row.  Nothing is written twice, so the output
+// needs no memset (the reference zero-fills it first, ms_deform_attn_cuda.cu:54).
+//
+// Work order.  CTAs walk "units" of 64 items with a grid-stride loop.  For encoder self-attention
+// (one query per pixel) a unit is an 8x8 tile of queries of one level and one head, so the gathers
+// of a CTA overlap in L1; otherwise units are consecutive items.  The choice is made on the device
+// from the int64 shape table (no host read of device memory).
+#include "msda_common.cuh"
+#include "msda_launch.h"
+
+namespace msda {
+
+template <typename VT, int D, int P, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr) {
+  constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
+  constexpr int LPG = D / CH;              // lanes per (item, level) group
+  constexpr int G = 32 / LPG;              // groups per warp
+  static_assert(D % CH == 0 && LPG >= 1 && LPG <= 32 && (LPG & (LPG - 1)) == 0, "unsupported head width");
+
+  __shared__ Tables tb;
+  load_tables(pr, tb);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / LPG, j = lane % LPG;
+  const int GI = min(G, pow2_ceil(pr.L));  // groups cooperating on one item
+  const int IPW = G / GI;                  // items per warp pass
+  const int rounds = (pr.L + GI - 1) / GI;
+  const int sub = g / GI, gi = g % GI;
+  const int MD = pr.M * D;
+
+  const VT *__restrict__ value = static_cast<const VT *>(pr.value);
+  const float *__restrict__ loc = static_cast<const float *>(pr.loc);
+  const float *__restrict__ attn = static_cast<const float *>(pr.attn);
+  VT *__restrict__ out = static_cast<VT *>(pr.out);
+
+  for (long long unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+    for (int k0 = warp * IPW; k0 < kUnitItems; k0 += (kThreads / 32) * IPW) {
+      const Item it = decode_item(pr, tb, unit, k0 + sub);
+      const long long item = ((long long)it.b * pr.Lq + it.q) * pr.M + it.m;
+
+      float acc[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+
+      for (int r = 0; r < rounds; ++r) {
+        const int l = r * GI + gi;
+        const bool act = it.valid && l < pr.L;
+        const int lc = act ? l : 0;
+        const int H = tb.H[lc], W = tb.W[lc];
+
+        // (x,y) pairs and weights of this level: P*8 + P*4 contiguous bytes, 16-byte aligned
+        float xy[2 * P], a[P];
+        {
+          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + (item * pr.L + lc) * (2 * P));
+          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + (item * pr.L + lc) * P);
+#pragma unroll
+          for (int v = 0; v < P / 2; ++v) {
+            const uint4 u = gather16(lp + v, act);
+            xy[4 * v + 0] = __uint_as_float(u.x); xy[4 * v + 1] = __uint_as_float(u.y);
+            xy[4 * v + 2] = __uint_as_float(u.z); xy[4 * v + 3] = __uint_as_float(u.w);
+          }
+#pragma unroll
+          for (int v = 0; v < P / 4; ++v) {
+            const uint4 u = gather16(ap + v, act);
+            a[4 * v + 0] = __uint_as_float(u.x); a[4 * v + 1] = __uint_as_float(u.y);
+            a[4 * v + 2] = __uint_as_float(u.z); a[4 * v + 3] = __uint_as_float(u.w);
+          }
+        }
+        const VT *slab = value + (((long long)it.b * pr.S + tb.start[lc]) * pr.M + it.m) * D + j * CH;
+
+        uint4 raw[P][4];
+        float wt[P][4];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+          const bool in = act && c.inside;
+          const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+          const float hh = 1.f - c.lh, hw = 1.f - c.lw;
+          const float aw = in ? a[p] : 0.f;
+          wt[p][0] = in ? hh * hw * aw : 0.f;
+          wt[p][1] = in ? hh * c.lw * aw : 0.f;
+          wt[p][2] = in ? c.lh * hw * aw : 0.f;
+          wt[p][3] = in ? c.lh * c.lw * aw : 0.f;
+          const int o00 = (c.h_low * W + c.w_low) * MD;
+          raw[p][0] = gather16(slab + o00, mask & 1);
+          raw[p][1] = gather16(slab + o00 + MD, mask & 2);
+          raw[p][2] = gather16(slab + o00 + W * MD, mask & 4);
+          raw[p][3] = gather16(slab + o00 + W * MD + MD, mask & 8);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            float v[CH];
+            Chan<VT>::unpack(raw[p][kk], v);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[c] = fmaf(wt[p][kk], v[c], acc[c]);
+          }
+        }
+      }
+
+      // combine the level groups of each item
+      for (int d = LPG; d < LPG * GI; d <<= 1) {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+      }
+      if (it.valid && gi == 0) {
+        *reinterpret_cast<uint4 *>(out + item * D + j * CH) = Chan<VT>::pack(acc);
+      }
+    }
+  }
+}
+
+template <typename VT, int D, int P>
+static cudaError_t launch_fwd_vec(const Problem &pr, int grid, cudaStream_t stream) {
+  fwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+  return cudaGetLastError();
+}
+
+template <typename VT>
+static int dispatch_fwd(const Problem &pr, int grid, cudaStream_t stream) {
+#define MSDA_CASE(DD, PP) \
+  if (pr.D == DD && pr.P == PP) return (int)launch_fwd_vec<VT, DD, PP>(pr, grid, stream);
+  MSDA_CASE(32, 4) MSDA_CASE(32, 8) MSDA_CASE(16, 4) MSDA_CASE(16, 8) MSDA_CASE(64, 4) MSDA_CASE(64, 8)
+#undef MSDA_CASE
+  return MSDA_E_UNSUPPORTED;
+}
+
+bool fwd_vec_supported(int dtype, int D, int P, int L) {
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+  if (!(D == 16 || D == 32 || D == 64)) return false;
+  if (!(P == 4 || P == 8)) return false;
+  return L >= 1 && L <= kMaxLevels;
+}
+
+int launch_forward_vec(const Problem &pr, int dtype, int grid, cudaStream_t stream) {
+  if (dtype == MSDA_F32) return dispatch_fwd<float>(pr, grid, stream);
+  if (dtype == MSDA_BF16) return dispatch_fwd<__nv_bfloat16>(pr, grid, stream);
+  return MSDA_E_UNSUPPORTED;
+}
+
+}  // namespace msda

@@ -1,0 +1,100 @@
+"""CPU-side checks (no compute calls): the C-ABI library loads and exports every symbol the public
+header declares, the Python mirror keeps the reference's names / init / error behaviour."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "msda_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msda_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from msda_b200 import _lib
+    names = _header_symbols()
+    assert sorted(_lib.EXPORTS) == names
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    assert _lib.lib().msda_abi_version() == _lib.ABI_VERSION
+    assert b"workspace" in _lib.lib().msda_error_string(-3)
+
+
+def test_argument_validation_without_a_gpu():
+    """Rejected calls return negative codes before any CUDA work is attempted."""
+    from msda_b200 import _lib
+    lib = _lib.lib()
+    assert lib.msda_forward(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 0, 0, None) == -1
+    assert lib.msda_backward_workspace_bytes(1, 10, 2, 32, 1, 5, 4, _lib.MSDA_F32, 0) == 0
+    assert lib.msda_backward_workspace_bytes(1, 10, 2, 32, 1, 5, 4, _lib.MSDA_BF16, 0) == 10 * 2 * 32 * 4
+    assert lib.msda_backward_workspace_bytes(0, 10, 2, 32, 1, 5, 4, _lib.MSDA_F32, 0) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from msda_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmsda_b200.so"))
+    with pytest.raises(_lib.MSDAError, match="no CPU/PyTorch fallback"):
+        _lib.lib()
+
+
+def test_cpu_tensors_raise_like_the_reference():
+    import MultiScaleDeformableAttention as MSDA
+    from msda_b200 import MSDeformAttnFunction
+    v = torch.zeros(1, 30, 2, 2)
+    sh, st = torch.tensor([[6, 4], [3, 2]]), torch.tensor([0, 24])
+    loc, at = torch.zeros(1, 2, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2, 2)
+    for fn in (lambda: MSDA.ms_deform_attn_forward(v, sh, st, loc, at, 2),
+               lambda: MSDA.ms_deform_attn_backward(v, sh, st, loc, at, torch.zeros(1, 2, 4), 2),
+               lambda: MSDeformAttnFunction.apply(v, sh, st, loc, at, 2)):
+        with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+            fn()
+
+
+def test_module_names_shapes_and_init():
+    from msda_b200 import MSDeformAttn, MultiScaleDeformableAttention
+    m = MSDeformAttn(256, 4, 8, 4)
+    assert sorted(m.state_dict()) == sorted(
+        f"{n}.{p}" for n in ("sampling_offsets", "attention_weights", "value_proj", "output_proj") for p in ("weight", "bias"))
+    assert m.sampling_offsets.weight.shape == (256, 256) and m.attention_weights.weight.shape == (128, 256)
+    assert m.im2col_step == 64
+    assert not m.sampling_offsets.weight.any() and not m.attention_weights.weight.any() and not m.attention_weights.bias.any()
+    bias = m.sampling_offsets.bias.detach().view(8, 4, 4, 2)
+    for h in range(8):
+        d = torch.tensor([math.cos(h * math.pi / 4), math.sin(h * math.pi / 4)])
+        d = d / d.abs().max()
+        for p in range(4):
+            assert torch.allclose(bias[h, :, p], (d * (p + 1)).expand(4, 2), atol=1e-6)
+    assert not m.value_proj.bias.any() and not m.output_proj.bias.any()
+    lim = math.sqrt(6.0 / 512)
+    assert m.value_proj.weight.abs().max() <= lim and m.value_proj.weight.std() > 0.5 * lim / math.sqrt(3)
+    with pytest.raises(ValueError):
+        MSDeformAttn(250, 4, 8, 4)
+    with pytest.warns(UserWarning):
+        MSDeformAttn(240, 4, 8, 4)
+    a = MultiScaleDeformableAttention(embed_dims=128, num_levels=3, num_heads=4, num_points=2, batch_first=True)
+    b = MultiScaleDeformableAttention(embed_dim=128, num_levels=3, num_heads=4, num_points=2, img2col_step=32)
+    assert a.d_model == b.d_model == 128 and b.im2col_step == 32 and a.batch_first and not b.batch_first
+    a.init_weights()
+
+
+def test_sampling_locations_forms():
+    from msda_b200.modules import sampling_locations_from
+    sh = torch.tensor([[4, 6], [2, 3]])
+    off = torch.randn(1, 5, 2, 2, 3, 2)
+    ref2 = torch.rand(1, 5, 2, 2)
+    loc = sampling_locations_from(ref2, off, sh, 3)
+    assert torch.allclose(loc[0, 1, 1, 1, 2], ref2[0, 1, 1] + off[0, 1, 1, 1, 2] / torch.tensor([3.0, 2.0]))
+    ref4 = torch.rand(1, 5, 2, 4)
+    loc = sampling_locations_from(ref4, off, sh, 3)
+    assert torch.allclose(loc[0, 2, 0, 1, 0], ref4[0, 2, 1, :2] + off[0, 2, 0, 1, 0] / 3 * ref4[0, 2, 1, 2:] * 0.5)
+    with pytest.raises(ValueError):
+        sampling_locations_from(torch.rand(1, 5, 2, 3), off, sh, 3)

@@ -1,0 +1,167 @@
+"""Drop-in behaviour of the Python mirror on the GPU: autograd Function, nn.Module, keyword adapter,
+AMP, checkpoint re-entrancy, edge inputs and the host-buffer C-ABI path."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import make_inputs
+from oracle import oracle, torch_port
+
+pytestmark = pytest.mark.gpu
+SHAPES = [(16, 22), (8, 11), (4, 6), (2, 3)]
+
+
+def _tables(shapes, device="cuda"):
+    sh = torch.as_tensor(shapes, dtype=torch.long, device=device)
+    st = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    return sh, st
+
+
+def test_function_apply_autograd_matches_port():
+    from msda_b200 import MSDeformAttnFunction
+    g = make_inputs(SHAPES, N=2, M=8, D=32, Lq=40, P=4, dist="W", seed=2)
+    sh, st = _tables(SHAPES)
+    v = torch.from_numpy(g["value"]).cuda().requires_grad_(True)
+    s = torch.from_numpy(g["loc"]).cuda().requires_grad_(True)
+    a = torch.from_numpy(g["attn"]).cuda().requires_grad_(True)
+    go = torch.from_numpy(g["grad_out"]).cuda()
+    out = MSDeformAttnFunction.apply(v, sh, st, s, a, 64)
+    out.backward(go)
+    ref = torch_port.fwd_bwd(v.detach().double(), SHAPES, s.detach().double(), a.detach().double(), go.double())
+    for got, want in zip((out, v.grad, a.grad), (ref[0], ref[1], ref[3])):
+        assert oracle.normwise(got.detach().cpu().numpy(), want.cpu().numpy()) < 1e-5
+    assert s.grad.shape == s.shape
+
+
+def _reference_style_forward(mod, query, ref_pts, src, sh, pad):
+    """The module's math with the op replaced by the grid_sample port (fp64)."""
+    from msda_b200.modules import sampling_locations_from
+    m = mod.double()
+    N, Lq, _ = query.shape
+    value = m.value_proj(src.double())
+    if pad is not None:
+        value = value.masked_fill(pad[..., None], 0.0)
+    value = value.view(N, src.shape[1], m.n_heads, -1)
+    off = m.sampling_offsets(query.double()).view(N, Lq, m.n_heads, m.n_levels, m.n_points, 2)
+    w = m.attention_weights(query.double()).view(N, Lq, m.n_heads, -1).softmax(-1).view(N, Lq, m.n_heads, m.n_levels, m.n_points)
+    loc = sampling_locations_from(ref_pts.double(), off, sh, m.n_points)
+    return m.output_proj(torch_port.msda_grid_sample(value, sh.tolist(), loc, w))
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_module_matches_reference_math(ref_dim):
+    import copy
+    from msda_b200 import MSDeformAttn
+    torch.manual_seed(0)
+    mod = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():   # leave the degenerate init so offsets/weights depend on the query
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    sh, st = _tables(SHAPES)
+    S = int(sh.prod(1).sum())
+    N, Lq = 2, 33
+    query = torch.randn(N, Lq, 256, device="cuda")
+    src = torch.randn(N, S, 256, device="cuda", requires_grad=True)
+    ref_pts = torch.rand(N, Lq, 4, ref_dim, device="cuda")
+    pad = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    pad[1, -7:] = True
+    out = mod(query, ref_pts, src, sh, st, pad)
+    out.square().mean().backward()
+    src64 = src.detach().double().requires_grad_(True)
+    want = _reference_style_forward(copy.deepcopy(mod), query, ref_pts, src64, sh, pad)
+    want.square().mean().backward()
+    assert oracle.normwise(out.detach().cpu().numpy(), want.detach().cpu().numpy()) < 2e-5
+    assert oracle.normwise(src.grad.cpu().numpy(), src64.grad.cpu().numpy()) < 5e-5
+
+
+def test_keyword_adapter_and_bf16_autocast_and_checkpoint():
+    from torch.utils.checkpoint import checkpoint
+    from msda_b200 import MultiScaleDeformableAttention
+    torch.manual_seed(1)
+    attn = MultiScaleDeformableAttention(embed_dims=256, num_levels=4, num_heads=8, num_points=4, batch_first=True).cuda()
+    attn.init_weights()
+    sh, st = _tables(SHAPES)
+    S = int(sh.prod(1).sum())
+    src = torch.randn(2, S, 256, device="cuda", requires_grad=True)
+    pos = torch.randn(2, S, 256, device="cuda")
+    ref_pts = torch.rand(2, S, 4, 2, device="cuda")
+    call = lambda x: attn(query=x + pos, reference_points=ref_pts, value=x, spatial_shapes=sh, level_start_index=st,
+                          key_padding_mask=None)
+    full = call(src)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        low = checkpoint(call, src, use_reentrant=False)
+    assert low.dtype == torch.bfloat16
+    low.float().square().mean().backward()
+    assert torch.isfinite(src.grad).all()
+    assert oracle.normwise(low.float().detach().cpu().numpy(), full.detach().cpu().numpy()) < 3e-2
+
+
+def test_fp16_branch_widens_like_reference():
+    from msda_b200 import MSDeformAttn
+    mod = MSDeformAttn(64, 2, 2, 4).cuda().half()
+    sh, st = _tables([(6, 4), (3, 2)])
+    q = torch.randn(1, 5, 64, device="cuda", dtype=torch.half)
+    src = torch.randn(1, 30, 64, device="cuda", dtype=torch.half)
+    out = mod(q, torch.rand(1, 5, 2, 2, device="cuda", dtype=torch.half), src, sh, st)
+    assert out.dtype == torch.float16 and torch.isfinite(out).all()
+
+
+def test_error_behaviour_matches_reference():
+    from msda_b200 import ms_deform_attn_forward
+    g = make_inputs([(6, 4), (3, 2)], N=3, M=2, D=4, Lq=5, P=2, dist="U")
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    v, sh, st, loc, at = t("value"), t("shapes"), t("starts"), t("loc"), t("attn")
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        ms_deform_attn_forward(v, sh, st, loc, at, 2)                     # 3 % 2 != 0  (.cu:52)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ms_deform_attn_forward(v.transpose(2, 3), sh, st, loc, at, 3)     # (.cu:28)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        ms_deform_attn_forward(v.cpu(), sh, st, loc, at, 3)               # (ms_deform_attn.h:38)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ms_deform_attn_forward(v, sh.cpu(), st, loc, at, 3)               # (.cu:35)
+    assert ms_deform_attn_forward(v, sh, st, loc, at, 1).shape == (3, 5, 8)
+
+
+def test_edge_inputs():
+    from msda_b200 import ms_deform_attn_backward, ms_deform_attn_forward
+    for D, P in ((32, 4), (5, 3)):
+        g = make_inputs([(6, 4), (3, 2)], N=2, M=2, D=D, Lq=9, P=P, dist="U", seed=4)
+        t = lambda k: torch.from_numpy(g[k]).cuda()
+        v, sh, st, at, go = t("value"), t("shapes"), t("starts"), t("attn"), t("grad_out")
+        far = torch.full_like(t("loc"), 7.0)                  # every sample rejected
+        out = ms_deform_attn_forward(v, sh, st, far, at, 64)
+        gv, gl, ga = ms_deform_attn_backward(v, sh, st, far, at, go, 64)
+        assert not out.any() and not gv.any() and not gl.any() and not ga.any()
+        nan = t("loc").clone()
+        nan[0, 0, 0, 0, 0, 0] = float("nan")                  # a NaN coordinate is rejected, not propagated
+        out = ms_deform_attn_forward(v, sh, st, nan, at, 64)
+        gv, gl, ga = ms_deform_attn_backward(v, sh, st, nan, at, go, 64)
+        assert all(torch.isfinite(x).all() for x in (out, gv, gl, ga))
+        assert gl[0, 0, 0, 0, 0].abs().sum() == 0 and ga[0, 0, 0, 0, 0] == 0
+        corners = t("loc").clone().fill_(0.0)
+        corners[..., 1::2, :] = 1.0                           # exactly 0 and exactly 1
+        want = oracle.forward(g["value"], g["shapes"], g["starts"], corners.cpu().numpy(), g["attn"], np.float64)
+        got = ms_deform_attn_forward(v, sh, st, corners, at, 64)
+        assert oracle.normwise(got.cpu().numpy(), want) < 1e-5
+
+
+def test_host_buffer_abi_path():
+    from msda_b200 import _lib
+    g = make_inputs(SHAPES, N=2, M=8, D=32, Lq=None, P=4, dist="W", seed=8)
+    N, S, M, D, L, Lq, P = g["dims"]
+    lib = _lib.lib()
+    ctx = ctypes.c_void_p()
+    _lib.check(lib.msda_host_create(ctypes.byref(ctx), N, S, M, D, L, Lq, P, _lib.MSDA_F32, _lib.MSDA_BWD_ATOMIC), "create")
+    out = np.empty((N, Lq, M * D), np.float32)
+    gv, gl, ga = np.empty_like(g["value"]), np.empty_like(g["loc"]), np.empty_like(g["attn"])
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for _ in range(2):
+        _lib.check(lib.msda_host_fwd_bwd(ctx, p(g["value"]), p(g["shapes"]), p(g["starts"]), p(g["loc"]), p(g["attn"]),
+                                         p(g["grad_out"]), p(out), p(gv), p(gl), p(ga)), "host_fwd_bwd")
+    assert lib.msda_host_h2d_bytes(ctx) > g["value"].nbytes and lib.msda_host_d2h_bytes(ctx) > out.nbytes
+    lib.msda_host_destroy(ctx)
+    want = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
+    wgv, wgl, wga = oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
+    assert oracle.normwise(out, want) < 1e-5 and oracle.normwise(gv, wgv) < 1e-5 and oracle.normwise(ga, wga) < 1e-5
