@@ -68,10 +68,11 @@ const char *msda_error_string(int code);
 /* Variant selector for experiments and A/B profiling; 0 = the library's default choice.
  * bit 0..3  : kernel family (1 = generic per-channel kernels, 2 = vector kernels, linear order,
  *             3 = vector kernels, query-tile order)
+ * bit 4..5  : CTAs/SM the vector kernels are register-limited for (0: 2, 1: 3, 2: 4)
  * bit 8      : (backward, atomic mode) MSDA_VARIANT_NO_ZERO   -- the caller has already zeroed the
  *             accumulator (grad_value, or the workspace for bf16); skip the memset
  * bit 9      : (backward, bf16)         MSDA_VARIANT_NO_NARROW -- leave the fp32 accumulator in the
- *             workspace and do not write grad_value; finish with msda_narrow_bf16()
+ *             workspace and do not write grad_value; finish with msda_backward_finish_bf16()
  *             (bits 8/9 let a profiler bracket the scatter kernel alone; same kernels, same order)
  * other bits: reserved, must be 0. */
 #define MSDA_VARIANT_NO_ZERO 0x100
@@ -93,8 +94,10 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
                   int num_query, int num_point, int value_dtype, int mode, int variant,
                   void *workspace, size_t workspace_bytes, void *stream);
 
-/* fp32 -> bf16 (round to nearest even) of n elements; the last stage of a bf16 backward. */
-int msda_narrow_bf16(const float *src, void *dst, size_t n, void *stream);
+/* Last stage of a bf16 backward that was launched with MSDA_VARIANT_NO_NARROW: rounds the fp32
+ * accumulator held in `workspace` (library-private row layout) to bf16 grad_value (N, S, M, D). */
+int msda_backward_finish_bf16(const void *workspace, void *grad_value, int batch, int spatial_size,
+                              int num_heads, int channels, void *stream);
 
 /* rec: int32 (N, Lq, M, L, P, 4) = [h_low, w_low, flags, slab_row]; flags bit0 = sample accepted,
  * bits1..4 = which of the 4 neighbours exist; slab_row = b*S + level_start_index[l].  fp32 path. */

@@ -32,7 +32,7 @@ int check_dims(int N, int S, int M, int D, int L, int Lq, int P, int dtype) {
   if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F64) return MSDA_E_INVALID;
   // in-slab offsets are 32-bit element indices (like the reference, cuh:47-53)
   if ((long long)S * M * D >= (1LL << 31)) return MSDA_E_TOO_LARGE;
-  if ((long long)N * Lq * M * L * P * 2 >= (1LL << 40)) return MSDA_E_TOO_LARGE;
+  if ((long long)N * Lq * M >= (1LL << 31) - 64 || (long long)N * S >= (1LL << 31)) return MSDA_E_TOO_LARGE;
   return MSDA_OK;
 }
 
@@ -46,12 +46,21 @@ int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool
   return (Lq == S) ? 3 : 2;
 }
 
-int vec_grid(const Problem &pr) {
-  // Persistent CTAs: 2 x 256 threads fit per SM at <=128 registers; 4 waves' worth of CTAs keeps
-  // the grid-stride tail short without a host read of the (device-resident) shape table.
+// The bf16 backward accumulates fp32 rows in the permuted channel order of acc_pos() whenever the head
+// width allows it; a function of (dtype, D) only, so every kernel family and the narrowing agree.
+bool acc_is_permuted(int dtype, int D) { return dtype == MSDA_BF16 && D % 8 == 0; }
+
+// variant bits 4..5: CTAs per SM the vector kernels are compiled for (0 -> 2, 1 -> 3, 2 -> 4)
+int min_blocks(int variant) { return 2 + ((variant >> 4) & 3) > 4 ? 4 : 2 + ((variant >> 4) & 3); }
+
+int vec_grid(const Problem &pr, int resident_per_sm) {
+  // Persistent CTAs: exactly as many as stay resident (the kernels are register-limited to
+  // `resident_per_sm` CTAs of 256 threads), each walking units with a grid-stride loop, so the table
+  // prologue runs once per CTA slot.  Capped by an upper bound of the unit count that needs no host
+  // read of the (device-resident) shape table.
   const long long items = (long long)pr.N * pr.Lq * pr.M;
   const long long upper = (items + kUnitItems - 1) / kUnitItems + (long long)pr.N * pr.M * 4 * pr.L + 64;
-  const long long want = (long long)sm_count() * 8;
+  const long long want = (long long)sm_count() * resident_per_sm;
   return (int)(upper < want ? upper : want);
 }
 
@@ -88,7 +97,7 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
   const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
   if (family == 1) return launch_forward_generic(pr, dtype, stream);
   pr.tiled = (family == 3);
-  return launch_forward_vec(pr, dtype, vec_grid(pr), stream);
+  return launch_forward_vec(pr, dtype, vec_grid(pr, min_blocks(variant)), min_blocks(variant), stream);
 }
 
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
@@ -128,6 +137,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 
   // atomic mode: accumulate into fp32 (fp64) -- grad_value itself, or the workspace for bf16
   void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
+  pr.acc_permuted = acc_is_permuted(dtype, D);
   const size_t acc_bytes = n_value * (dtype == MSDA_F64 ? 8 : 4);
   if (!(variant & MSDA_VARIANT_NO_ZERO))
     if (cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, stream)) return (int)e;
@@ -142,18 +152,18 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     rc = launch_backward_generic(pr, dtype, stream);
   } else {
     pr.tiled = (family == 3);
-    rc = launch_backward_vec(pr, dtype, vec_grid(pr), stream);
+    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant)), min_blocks(variant), stream);
   }
   if (rc != MSDA_OK) return rc;
-  if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW)) rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, stream);
+  if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW))
+    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0, stream);
   return rc;
 }
 
-int msda_narrow_bf16(const float *src, void *dst, size_t n, void *stream_) {
-  if (!src || !dst) return MSDA_E_INVALID;
-  if (n == 0) return MSDA_OK;
-  if (!aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return MSDA_E_INVALID;
-  return launch_f32_to_bf16(src, dst, (long long)n, static_cast<cudaStream_t>(stream_));
+int msda_backward_finish_bf16(const void *workspace, void *grad_value, int N, int S, int M, int D, void *stream_) {
+  if (!workspace || !grad_value || N <= 0 || S <= 0 || M <= 0 || D <= 0) return MSDA_E_INVALID;
+  return launch_f32_to_bf16(static_cast<const float *>(workspace), grad_value, (long long)N * S * M * D, D,
+                            acc_is_permuted(MSDA_BF16, D), static_cast<cudaStream_t>(stream_));
 }
 
 int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index, const float *sampling_loc,

@@ -50,6 +50,7 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 template <typename VT, int D, int P, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;
+  constexpr int NP = Chan<VT>::kPairs;
   constexpr int LPG = D / CH;
   constexpr int G = 32 / LPG;
   constexpr int NV = 4 * P;                       // dot products per (item, level)
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   const int rounds = (pr.L + GI - 1) / GI;
   const int sub = g / GI, gi = g % GI;
   const int MD = pr.M * D;
+  const int LP2 = pr.L * 2 * P, LP1 = pr.L * P;
 
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
   const VT *__restrict__ grad_out = static_cast<const VT *>(pr.grad_out);
@@ -74,13 +76,14 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   float *__restrict__ grad_loc = static_cast<float *>(pr.grad_loc);
   float *__restrict__ grad_attn = static_cast<float *>(pr.grad_attn);
 
-  for (long long unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+  for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+    const UnitCtx uc = decode_unit(pr, tb, unit);
     for (int k0 = warp * IPW; k0 < kUnitItems; k0 += (kThreads / 32) * IPW) {
-      const Item it = decode_item(pr, tb, unit, k0 + sub);
-      const long long item = ((long long)it.b * pr.Lq + it.q) * pr.M + it.m;
+      const Item it = decode_item(pr, tb, uc, k0 + sub);
+      const long long item = it.item;
 
-      float go[CH];
-      Chan<VT>::unpack(gather16(grad_out + item * D + j * CH, it.valid), go);
+      unsigned long long go[NP];
+      Chan<VT>::unpack2(gather16(grad_out + item * D + j * CH, it.valid), go);
 
       for (int r = 0; r < rounds; ++r) {
         const int l = r * GI + gi;
@@ -90,8 +93,8 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
         float xy[2 * P], a[P];
         {
-          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + (item * pr.L + lc) * (2 * P));
-          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + (item * pr.L + lc) * P);
+          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + item * LP2 + lc * (2 * P));
+          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + item * LP1 + lc * P);
 #pragma unroll
           for (int v = 0; v < P / 2; ++v) {
             const uint4 u = gather16(lp + v, act);
@@ -105,12 +108,37 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             a[4 * v + 2] = __uint_as_float(u.z); a[4 * v + 3] = __uint_as_float(u.w);
           }
         }
-        const long long slab_off = (((long long)it.b * pr.S + tb.start[lc]) * pr.M + it.m) * D + j * CH;
-        const VT *slab = value + slab_off;
-        float *gslab = gacc + slab_off;
+        const long long row_off = (long long)(it.b * pr.S + tb.start[lc]) * MD + it.m * D;
+        const VT *slab = value + row_off + j * CH;
+        // fp32 accumulator row of this head.  fp32 value: natural channel order (it IS grad_value).
+        // bf16 value: the row is stored as [first halves of every lane's 8 channels | second halves]
+        // (acc_pos() in msda_common.cuh) so each 16-byte reduction of a 4-lane group lands in ONE
+        // fully-used 64-byte span instead of half of every 32-byte sector.
+        float *gslab = gacc + row_off + j * 4;
+        const int WMD = W * MD;
 
         float d[NV];
         float g_lh[P], g_lw[P], g_aw[P];
+        // pending grad_value contribution: consecutive points that fall into the same cell are summed
+        // in registers and sent as one set of reductions (warp-level aggregation before the L2 atomics)
+        float pend[4] = {0.f, 0.f, 0.f, 0.f};
+        int pend_off = 0, pend_mask = 0;
+        auto flush = [&]() {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int off = pend_off + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
+            if (((pend_mask >> kk) & 1) && pend[kk] != 0.f) {
+              const unsigned long long c2 = pack_f2(pend[kk], pend[kk]);
+#pragma unroll
+              for (int h4 = 0; h4 < NP / 2; ++h4) {
+                float r0, r1, r2, r3;
+                unpack_f2(fmul2(c2, go[2 * h4]), r0, r1);
+                unpack_f2(fmul2(c2, go[2 * h4 + 1]), r2, r3);
+                red_add_f32x4(gslab + off + h4 * (D / 2), r0, r1, r2, r3);
+              }
+            }
+          }
+        };
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
@@ -120,33 +148,42 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
           g_lw[p] = in ? c.lw : 0.f;
           g_aw[p] = in ? a[p] : 0.f;
           const float hh = 1.f - g_lh[p], hw = 1.f - g_lw[p];
-          const float cw[4] = {hh * hw * g_aw[p], hh * g_lw[p] * g_aw[p], g_lh[p] * hw * g_aw[p],
-                               g_lh[p] * g_lw[p] * g_aw[p]};
-          const int o00 = (c.h_low * W + c.w_low) * MD;
-          const int off[4] = {o00, o00 + MD, o00 + W * MD, o00 + W * MD + MD};
+          const float ah = hh * g_aw[p], al = g_lh[p] * g_aw[p];
+          const float cw[4] = {ah * hw, ah * g_lw[p], al * hw, al * g_lw[p]};
+          const int o00 = in ? c.h_low * WMD + c.w_low * MD : 0;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const bool on = (mask >> kk) & 1;
-            float v[CH];
-            Chan<VT>::unpack(gather16(slab + off[kk], on), v);
-            float dot = 0.f;
+            const int off = o00 + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
+            unsigned long long v[NP];
+            Chan<VT>::unpack2(gather16(slab + off, on), v);
+            unsigned long long dot2 = 0ull;
 #pragma unroll
-            for (int cidx = 0; cidx < CH; ++cidx) dot = fmaf(go[cidx], v[cidx], dot);
-            d[4 * p + kk] = dot;
-            if (on) {
+            for (int cidx = 0; cidx < NP; ++cidx) dot2 = ffma2(go[cidx], v[cidx], dot2);
+            float dlo, dhi;
+            unpack_f2(dot2, dlo, dhi);
+            d[4 * p + kk] = dlo + dhi;
+          }
+          // same cell <=> same offset AND same neighbour mask: (h, W-1) and (h+1, -1) share the
+          // row-major offset but never the mask
+          if (p > 0 && in && mask == pend_mask && o00 == pend_off) {
 #pragma unroll
-              for (int h4 = 0; h4 < CH / 4; ++h4)
-                red_add_f32x4(gslab + off[kk] + 4 * h4, cw[kk] * go[4 * h4], cw[kk] * go[4 * h4 + 1],
-                              cw[kk] * go[4 * h4 + 2], cw[kk] * go[4 * h4 + 3]);
-            }
+            for (int kk = 0; kk < 4; ++kk) pend[kk] += cw[kk];
+          } else {
+            if (p > 0) flush();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) pend[kk] = cw[kk];
+            pend_off = o00;
+            pend_mask = mask;
           }
         }
+        flush();
 
         reduce_scatter<NV, LPG / 2>(d, j);
 
         // Which point(s) this lane now owns, and with which of the four dot products.
-        float *gl = grad_loc + (item * pr.L + lc) * (2 * P);
-        float *ga = grad_attn + (item * pr.L + lc) * P;
+        float *gl = grad_loc + item * LP2 + lc * (2 * P);
+        float *ga = grad_attn + item * LP1 + lc * P;
         if constexpr (C >= 4) {
 #pragma unroll
           for (int t = 0; t < C / 4; ++t) {
@@ -203,52 +240,75 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 }
 
 template <typename VT, int D, int P>
-static cudaError_t launch_bwd_vec(const Problem &pr, int grid, cudaStream_t stream) {
-  bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
-  return cudaGetLastError();
+static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
+  if (minb == 4) bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
+  else if (minb == 3) bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
+  else bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+  return (int)cudaGetLastError();
 }
 
 template <typename VT>
-static int dispatch_bwd(const Problem &pr, int grid, cudaStream_t stream) {
+static int dispatch_bwd(const Problem &pr, int grid, int minb, cudaStream_t stream) {
 #define MSDA_CASE(DD, PP) \
-  if (pr.D == DD && pr.P == PP) return (int)launch_bwd_vec<VT, DD, PP>(pr, grid, stream);
+  if (pr.D == DD && pr.P == PP) return launch_bwd_vec<VT, DD, PP>(pr, grid, minb, stream);
   MSDA_CASE(32, 4) MSDA_CASE(32, 8) MSDA_CASE(16, 4) MSDA_CASE(16, 8) MSDA_CASE(64, 4) MSDA_CASE(64, 8)
 #undef MSDA_CASE
   return MSDA_E_UNSUPPORTED;
 }
 
-int launch_backward_vec(const Problem &pr, int dtype, int grid, cudaStream_t stream) {
-  if (dtype == MSDA_F32) return dispatch_bwd<float>(pr, grid, stream);
-  if (dtype == MSDA_BF16) return dispatch_bwd<__nv_bfloat16>(pr, grid, stream);
+int launch_backward_vec(const Problem &pr, int dtype, int grid, int minb, cudaStream_t stream) {
+  if (dtype == MSDA_F32) return dispatch_bwd<float>(pr, grid, minb, stream);
+  if (dtype == MSDA_BF16) return dispatch_bwd<__nv_bfloat16>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;
 }
 
 // ---- fp32 accumulator -> bf16 ------------------------------------------------------------------
-__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float4 *__restrict__ src, uint2 *__restrict__ dst,
-                                                         long long n4) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+// PERM: the accumulator rows use the permuted channel order of acc_pos() (bf16 value, D % 8 == 0).
+// One thread produces 8 consecutive bf16 channels (16 bytes) from two 16-byte accumulator chunks.
+template <bool PERM>
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ src, uint4 *__restrict__ dst,
+                                                         long long n8, int D) {
+  const int lanes = D / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = src[i];
-    dst[i] = make_uint2(Chan<__nv_bfloat16>::pack2(v.x, v.y), Chan<__nv_bfloat16>::pack2(v.z, v.w));
+    float4 a, b;
+    if (PERM) {
+      const long long row = i / lanes;
+      const int j = (int)(i - row * lanes);
+      const float *r = src + row * D;
+      a = *reinterpret_cast<const float4 *>(r + 4 * j);
+      b = *reinterpret_cast<const float4 *>(r + D / 2 + 4 * j);
+    } else {
+      a = *reinterpret_cast<const float4 *>(src + 8 * i);
+      b = *reinterpret_cast<const float4 *>(src + 8 * i + 4);
+    }
+    dst[i] = make_uint4(Chan<__nv_bfloat16>::pack2(a.x, a.y), Chan<__nv_bfloat16>::pack2(a.z, a.w),
+                        Chan<__nv_bfloat16>::pack2(b.x, b.y), Chan<__nv_bfloat16>::pack2(b.z, b.w));
   }
 }
 
-__global__ void f32_to_bf16_tail_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
-                                        long long first, long long n) {
-  const long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+__global__ void f32_to_bf16_scalar_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
+                                          long long first, long long n) {
+  for (long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
 }
 
-int launch_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t stream) {
-  const long long n4 = n / 4;
-  if (n4 > 0) {
-    const long long blocks = (n4 + 255) / 256;
+int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, cudaStream_t stream) {
+  const bool vec = (D % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+  if (vec) {
+    const long long n8 = n / 8;
+    const long long blocks = (n8 + 255) / 256;
     const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
-    f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(src),
-                                                 reinterpret_cast<uint2 *>(dst), n4);
+    if (permuted) f32_to_bf16_kernel<true><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
+    else f32_to_bf16_kernel<false><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
+  } else {
+    if (permuted) return MSDA_E_UNSUPPORTED;
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
+    f32_to_bf16_scalar_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), 0, n);
   }
-  if (n4 * 4 < n)
-    f32_to_bf16_tail_kernel<<<1, 32, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), n4 * 4, n);
   return (int)cudaGetLastError();
 }
 

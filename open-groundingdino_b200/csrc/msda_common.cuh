@@ -1,12 +1,15 @@
 // msda_common.cuh -- shared device code of libmsda_b200 (sm_100a only).
 //
 // Arithmetic contract (what "bit-exact sampling index" means here): the pixel coordinate of a
-// sample is fl32(fl32(loc * size) - 0.5f), the sample is used iff
-// h > -1 && w > -1 && h < H && w < W, and low = (int)floorf(coord).  That is the value set the
-// reference kernels produce (ms_deform_im2col_cuda.cuh:285-288 and :38-41; the reference subtracts a
-// double 0.5 from the rounded float product, which rounds to the same float -- see
-// tests/test_oracle_cpu.py::test_fp32_coordinate_is_mul_then_sub).  __fmul_rn/__fsub_rn keep ptxas
-// from contracting the pair into an FMA, which would change 1-10 % of coordinates.
+// sample is the single-rounded fl32(loc * size - 0.5), i.e. fmaf(loc, (float)size, -0.5f); the sample is
+// used iff h > -1 && w > -1 && h < H && w < W, and low = (int)floorf(coord).  That is what the
+// reference kernels compute AS COMPILED for this GPU: the source reads `loc_h * spatial_h - 0.5`
+// (ms_deform_im2col_cuda.cuh:285-286, inside test :288, floor :38-41) and nvcc 12.9 -O3 folds the
+// double literal away and contracts the pair into `FFMA R, loc, size, -0.5` in the forward and in
+// every backward kernel (cuobjdump of oracle/_ref/msda_ref_cuda.so; excerpt in
+// profiles/reference_sass_coordinate.txt).  An unfused multiply-then-subtract differs in 1-10 % of
+// coordinates and moves samples that sit on integer pixel coordinates into the neighbouring cell,
+// which changes grad_sampling_loc by O(1) there (tests/test_gpu_vs_reference_cuda.py).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -36,7 +39,16 @@ struct Problem {
   int N, S, M, D, L, Lq, P;
   int tiled;               // 1: enumerate queries as 2-D tiles of their own pyramid level
   int tile_w_log2;         // tile is (kUnitItems >> tile_w_log2) rows x (1 << tile_w_log2) columns
+  int acc_permuted;        // backward, bf16 value: accumulator rows use acc_pos() order
 };
+
+// Position of channel c inside a head's fp32 accumulator row when the row is permuted (bf16 value,
+// D % 8 == 0): lane j = c / 8 owns channels 8j..8j+7; its first four go to [4j, 4j+4), its last four
+// to [D/2 + 4j, D/2 + 4j + 4).
+__host__ __device__ inline int acc_pos(int c, int D) {
+  const int j = c >> 3, t = c & 7;
+  return t < 4 ? 4 * j + t : D / 2 + 4 * j + (t - 4);
+}
 
 // Per-CTA copy of the pyramid tables, narrowed to int like the reference does (cuh:274-277).
 struct Tables {
@@ -47,19 +59,26 @@ struct Tables {
   int tiles_x[kMaxLevels];
   int tile_first[kMaxLevels + 1];
   int n_tiles;                 // tiles per batch element (tiled order) -- 0 if tiling is off
-  long long n_units;           // work units in the whole launch
+  int n_items;                 // N * Lq * M
+  int n_units;                 // work units in the whole launch
 };
 
 __device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb) {
+  // one thread per level fetches its three int64 entries (independent loads, one round trip) ...
+  if (threadIdx.x < pr.L) {
+    const int l = threadIdx.x;
+    tb.H[l] = (int)pr.shapes[2 * l];
+    tb.W[l] = (int)pr.shapes[2 * l + 1];
+    tb.start[l] = (int)pr.starts[l];
+  }
+  __syncthreads();
+  // ... then one thread derives the prefix tables from shared memory
   if (threadIdx.x == 0) {
     const int tw = 1 << pr.tile_w_log2, th = kUnitItems >> pr.tile_w_log2;
     long long area = 0;
     int tiles = 0;
     for (int l = 0; l < pr.L; ++l) {
-      const int H = (int)pr.shapes[2 * l], W = (int)pr.shapes[2 * l + 1];
-      tb.H[l] = H;
-      tb.W[l] = W;
-      tb.start[l] = (int)pr.starts[l];
+      const int H = tb.H[l], W = tb.W[l];
       tb.qstart[l] = (int)area;
       tb.tiles_x[l] = (W + tw - 1) / tw;
       tb.tile_first[l] = tiles;
@@ -71,8 +90,8 @@ __device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb) {
     // one pixel per query.  Otherwise fall back to the natural (b, q, m) order.
     const bool tiled = pr.tiled && area == (long long)pr.Lq;
     tb.n_tiles = tiled ? tiles : 0;
-    const long long items = (long long)pr.N * pr.Lq * pr.M;
-    tb.n_units = tiled ? (long long)pr.N * tiles * pr.M : (items + kUnitItems - 1) / kUnitItems;
+    tb.n_items = pr.N * pr.Lq * pr.M;      // < 2^31, checked by the host
+    tb.n_units = tiled ? pr.N * tiles * pr.M : (tb.n_items + kUnitItems - 1) / kUnitItems;
   }
   __syncthreads();
 }
@@ -80,33 +99,65 @@ __device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb) {
 // One (query, head) item of a work unit.
 struct Item {
   int b, q, m;
+  int item;      // ((b * Lq) + q) * M + m
   bool valid;
 };
 
-// unit -> (b, tile, m); k in [0, kUnitItems) -> query inside the tile.  Consecutive units share the
-// tile and differ in head, so CTAs running at the same time touch the same pixels' other heads.
-__device__ __forceinline__ Item decode_item(const Problem &pr, const Tables &tb, long long unit, int k) {
-  Item it;
+// Everything about a work unit that does not depend on the item inside it.  Decoded once per unit
+// (the divisions live here), so the per-item cost is a handful of integer ops.
+struct UnitCtx {
+  int b, m;              // tiled order: fixed per unit
+  int y0, x0, Hq, Wq;    // tiled order: tile origin and the query level's extent
+  int q0;                // tiled order: first query of that level
+  int idx0;              // linear order: first item of the unit
+};
+
+// unit -> (b, tile, m).  Consecutive units share the tile and differ in head, so CTAs running at
+// the same time touch the same pixels' other heads (adjacent 64/128-byte rows in HBM).
+__device__ __forceinline__ UnitCtx decode_unit(const Problem &pr, const Tables &tb, int unit) {
+  UnitCtx uc;
   if (tb.n_tiles > 0) {
-    it.m = (int)(unit % pr.M);
-    const long long rest = unit / pr.M;
-    const int t = (int)(rest % tb.n_tiles);
-    it.b = (int)(rest / tb.n_tiles);
+    const unsigned u = (unsigned)unit, Mu = (unsigned)pr.M, T = (unsigned)tb.n_tiles;
+    uc.m = (int)(u % Mu);
+    const unsigned rest = u / Mu;
+    const int t = (int)(rest % T);
+    uc.b = (int)(rest / T);
     int l = 0;
     while (l + 1 < pr.L && t >= tb.tile_first[l + 1]) ++l;
     const int tl = t - tb.tile_first[l];
     const int ty = tl / tb.tiles_x[l], tx = tl - ty * tb.tiles_x[l];
-    const int y = (ty * (kUnitItems >> pr.tile_w_log2)) + (k >> pr.tile_w_log2);
-    const int x = (tx << pr.tile_w_log2) + (k & ((1 << pr.tile_w_log2) - 1));
-    it.valid = (y < tb.H[l]) && (x < tb.W[l]);
-    it.q = tb.qstart[l] + y * tb.W[l] + x;
+    uc.y0 = ty * (kUnitItems >> pr.tile_w_log2);
+    uc.x0 = tx << pr.tile_w_log2;
+    uc.Hq = tb.H[l];
+    uc.Wq = tb.W[l];
+    uc.q0 = tb.qstart[l];
+    uc.idx0 = 0;
   } else {
-    const long long idx = unit * kUnitItems + k;
-    it.valid = idx < (long long)pr.N * pr.Lq * pr.M;
-    it.m = (int)(idx % pr.M);
-    const long long r = idx / pr.M;
-    it.q = (int)(r % pr.Lq);
-    it.b = (int)(r / pr.Lq);
+    uc.b = uc.m = uc.y0 = uc.x0 = uc.Hq = uc.Wq = uc.q0 = 0;
+    uc.idx0 = unit * kUnitItems;
+  }
+  return uc;
+}
+
+// k in [0, kUnitItems) -> item of the unit.
+__device__ __forceinline__ Item decode_item(const Problem &pr, const Tables &tb, const UnitCtx &uc, int k) {
+  Item it;
+  if (tb.n_tiles > 0) {
+    const int y = uc.y0 + (k >> pr.tile_w_log2);
+    const int x = uc.x0 + (k & ((1 << pr.tile_w_log2) - 1));
+    it.valid = (y < uc.Hq) && (x < uc.Wq);
+    it.b = uc.b;
+    it.m = uc.m;
+    it.q = uc.q0 + y * uc.Wq + x;
+    it.item = (it.b * pr.Lq + it.q) * pr.M + it.m;
+  } else {
+    const unsigned idx = (unsigned)(uc.idx0 + k);
+    it.valid = idx < (unsigned)tb.n_items;
+    it.item = (int)idx;
+    it.m = (int)(idx % (unsigned)pr.M);
+    const unsigned r = idx / (unsigned)pr.M;
+    it.b = (int)(r / (unsigned)pr.Lq);
+    it.q = (int)(r - (unsigned)it.b * (unsigned)pr.Lq);
   }
   return it;
 }
@@ -121,8 +172,8 @@ struct Cell {
 
 __device__ __forceinline__ Cell<float> locate(float x, float y, int H, int W) {
   Cell<float> c;
-  const float h = __fsub_rn(__fmul_rn(y, (float)H), 0.5f);
-  const float w = __fsub_rn(__fmul_rn(x, (float)W), 0.5f);
+  const float h = __fmaf_rn(y, (float)H, -0.5f);
+  const float w = __fmaf_rn(x, (float)W, -0.5f);
   c.inside = (h > -1.0f) && (w > -1.0f) && (h < (float)H) && (w < (float)W);
   const float hf = floorf(h), wf = floorf(w);
   c.h_low = (int)hf;
@@ -154,6 +205,32 @@ __device__ __forceinline__ int corner_mask(int h_low, int w_low, int H, int W) {
          ((int)(bottom && right) << 3);
 }
 
+// Packed fp32x2 math (sm_100+: one FFMA2 issue slot for two lanes of the accumulator).
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b,
+                                                    unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ---- 16-byte channel vectors ---------------------------------------------------------------------
 template <typename VT>
 struct Chan;
@@ -168,6 +245,11 @@ struct Chan<float> {
   static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
   }
+  static constexpr int kPairs = 2;
+  static __device__ __forceinline__ void unpack2(const uint4 &u, unsigned long long (&p)[2]) {
+    p[0] = pack_f2(__uint_as_float(u.x), __uint_as_float(u.y));
+    p[1] = pack_f2(__uint_as_float(u.z), __uint_as_float(u.w));
+  }
 };
 
 template <>
@@ -179,6 +261,13 @@ struct Chan<__nv_bfloat16> {
     f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
     f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
     f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+  static constexpr int kPairs = 4;
+  static __device__ __forceinline__ void unpack2(const uint4 &u, unsigned long long (&p)[4]) {
+    p[0] = pack_f2(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u));
+    p[1] = pack_f2(__uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    p[2] = pack_f2(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u));
+    p[3] = pack_f2(__uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
   }
   static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);

@@ -6,9 +6,10 @@
 // whole 128-byte (fp32) or 64-byte (bf16) head rows.  The groups of a warp are spread over the
 // pyramid levels of an item: each group preloads the P (x,y) pairs and P attention weights of its
 // level with two or three 16-byte loads, computes the bilinear geometry in registers and issues the
-// 4*P corner gathers back to back; the per-level partial sums are combined with xor-shuffles and one
-// lane group stores the 16-byte chunks of the output row.  Nothing is written twice, so the output
-// needs no memset (the reference zero-fills it first, ms_deform_attn_cuda.cu:54).
+// 4*P corner gathers back to back; the accumulation is packed fp32x2 (FFMA2); the per-level partial
+// sums are combined with xor-shuffles and one lane group stores the 16-byte chunks of the output
+// row.  Nothing is written twice, so the output needs no memset (the reference zero-fills it first,
+// ms_deform_attn_cuda.cu:54).
 //
 // Work order.  CTAs walk "units" of 64 items with a grid-stride loop.  For encoder self-attention
 // (one query per pixel) a unit is an 8x8 tile of queries of one level and one head, so the gathers
@@ -22,6 +23,7 @@ namespace msda {
 template <typename VT, int D, int P, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
+  constexpr int NP = Chan<VT>::kPairs;     // fp32x2 accumulators per lane
   constexpr int LPG = D / CH;              // lanes per (item, level) group
   constexpr int G = 32 / LPG;              // groups per warp
   static_assert(D % CH == 0 && LPG >= 1 && LPG <= 32 && (LPG & (LPG - 1)) == 0, "unsupported head width");
@@ -36,20 +38,21 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
   const int rounds = (pr.L + GI - 1) / GI;
   const int sub = g / GI, gi = g % GI;
   const int MD = pr.M * D;
+  const int LP2 = pr.L * 2 * P, LP1 = pr.L * P;
 
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
   const float *__restrict__ loc = static_cast<const float *>(pr.loc);
   const float *__restrict__ attn = static_cast<const float *>(pr.attn);
   VT *__restrict__ out = static_cast<VT *>(pr.out);
 
-  for (long long unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+  for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+    const UnitCtx uc = decode_unit(pr, tb, unit);
     for (int k0 = warp * IPW; k0 < kUnitItems; k0 += (kThreads / 32) * IPW) {
-      const Item it = decode_item(pr, tb, unit, k0 + sub);
-      const long long item = ((long long)it.b * pr.Lq + it.q) * pr.M + it.m;
+      const Item it = decode_item(pr, tb, uc, k0 + sub);
 
-      float acc[CH];
+      unsigned long long acc[NP];
 #pragma unroll
-      for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+      for (int c = 0; c < NP; ++c) acc[c] = 0ull;
 
       for (int r = 0; r < rounds; ++r) {
         const int l = r * GI + gi;
@@ -60,8 +63,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         // (x,y) pairs and weights of this level: P*8 + P*4 contiguous bytes, 16-byte aligned
         float xy[2 * P], a[P];
         {
-          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + (item * pr.L + lc) * (2 * P));
-          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + (item * pr.L + lc) * P);
+          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + (long long)it.item * LP2 + lc * (2 * P));
+          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + (long long)it.item * LP1 + lc * P);
 #pragma unroll
           for (int v = 0; v < P / 2; ++v) {
             const uint4 u = gather16(lp + v, act);
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
             a[4 * v + 2] = __uint_as_float(u.z); a[4 * v + 3] = __uint_as_float(u.w);
           }
         }
-        const VT *slab = value + (((long long)it.b * pr.S + tb.start[lc]) * pr.M + it.m) * D + j * CH;
+        const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
+        const int WMD = W * MD;
 
         uint4 raw[P][4];
         float wt[P][4];
@@ -84,52 +88,57 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
           const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
           const bool in = act && c.inside;
           const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          const float hh = 1.f - c.lh, hw = 1.f - c.lw;
           const float aw = in ? a[p] : 0.f;
-          wt[p][0] = in ? hh * hw * aw : 0.f;
-          wt[p][1] = in ? hh * c.lw * aw : 0.f;
-          wt[p][2] = in ? c.lh * hw * aw : 0.f;
-          wt[p][3] = in ? c.lh * c.lw * aw : 0.f;
-          const int o00 = (c.h_low * W + c.w_low) * MD;
-          raw[p][0] = gather16(slab + o00, mask & 1);
-          raw[p][1] = gather16(slab + o00 + MD, mask & 2);
-          raw[p][2] = gather16(slab + o00 + W * MD, mask & 4);
-          raw[p][3] = gather16(slab + o00 + W * MD + MD, mask & 8);
+          const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float ah = hh * aw, al = lh * aw;
+          wt[p][0] = ah * hw; wt[p][1] = ah * lw; wt[p][2] = al * hw; wt[p][3] = al * lw;
+          const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
+          raw[p][0] = gather16(p00, mask & 1);
+          raw[p][1] = gather16(p00 + MD, mask & 2);
+          raw[p][2] = gather16(p00 + WMD, mask & 4);
+          raw[p][3] = gather16(p00 + WMD + MD, mask & 8);
         }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            float v[CH];
-            Chan<VT>::unpack(raw[p][kk], v);
+            unsigned long long v[NP];
+            Chan<VT>::unpack2(raw[p][kk], v);
+            const unsigned long long w2 = pack_f2(wt[p][kk], wt[p][kk]);
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[c] = fmaf(wt[p][kk], v[c], acc[c]);
+            for (int c = 0; c < NP; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
           }
         }
       }
 
+      float res[CH];
+#pragma unroll
+      for (int c = 0; c < NP; ++c) unpack_f2(acc[c], res[2 * c], res[2 * c + 1]);
       // combine the level groups of each item
       for (int d = LPG; d < LPG * GI; d <<= 1) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+        for (int c = 0; c < CH; ++c) res[c] += __shfl_xor_sync(0xffffffffu, res[c], d);
       }
       if (it.valid && gi == 0) {
-        *reinterpret_cast<uint4 *>(out + item * D + j * CH) = Chan<VT>::pack(acc);
+        *reinterpret_cast<uint4 *>(out + (long long)it.item * D + j * CH) = Chan<VT>::pack(res);
       }
     }
   }
 }
 
 template <typename VT, int D, int P>
-static cudaError_t launch_fwd_vec(const Problem &pr, int grid, cudaStream_t stream) {
-  fwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
-  return cudaGetLastError();
+static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
+  if (minb == 4) fwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
+  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
+  else fwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+  return (int)cudaGetLastError();
 }
 
 template <typename VT>
-static int dispatch_fwd(const Problem &pr, int grid, cudaStream_t stream) {
+static int dispatch_fwd(const Problem &pr, int grid, int minb, cudaStream_t stream) {
 #define MSDA_CASE(DD, PP) \
-  if (pr.D == DD && pr.P == PP) return (int)launch_fwd_vec<VT, DD, PP>(pr, grid, stream);
+  if (pr.D == DD && pr.P == PP) return launch_fwd_vec<VT, DD, PP>(pr, grid, minb, stream);
   MSDA_CASE(32, 4) MSDA_CASE(32, 8) MSDA_CASE(16, 4) MSDA_CASE(16, 8) MSDA_CASE(64, 4) MSDA_CASE(64, 8)
 #undef MSDA_CASE
   return MSDA_E_UNSUPPORTED;
@@ -142,9 +151,9 @@ bool fwd_vec_supported(int dtype, int D, int P, int L) {
   return L >= 1 && L <= kMaxLevels;
 }
 
-int launch_forward_vec(const Problem &pr, int dtype, int grid, cudaStream_t stream) {
-  if (dtype == MSDA_F32) return dispatch_fwd<float>(pr, grid, stream);
-  if (dtype == MSDA_BF16) return dispatch_fwd<__nv_bfloat16>(pr, grid, stream);
+int launch_forward_vec(const Problem &pr, int dtype, int grid, int minb, cudaStream_t stream) {
+  if (dtype == MSDA_F32) return dispatch_fwd<float>(pr, grid, minb, stream);
+  if (dtype == MSDA_BF16) return dispatch_fwd<__nv_bfloat16>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;
 }
 

@@ -111,10 +111,11 @@ __global__ void __launch_bounds__(kGenericThreads) bwd_generic_kernel(const Prob
         for (int c = lane; c < pr.D; c += 32) {
           const CT top = load_as<VT, CT>(grad_out, item * pr.D + c);
           const CT tgv = top * a;
-          if (mask & 1) { d1 += top * load_as<VT, CT>(value, o00 + c); atomicAdd(gacc + o00 + c, hh * hw * tgv); }
-          if (mask & 2) { d2 += top * load_as<VT, CT>(value, o00 + MD + c); atomicAdd(gacc + o00 + MD + c, hh * lw * tgv); }
-          if (mask & 4) { d3 += top * load_as<VT, CT>(value, o00 + W * MD + c); atomicAdd(gacc + o00 + W * MD + c, lh * hw * tgv); }
-          if (mask & 8) { d4 += top * load_as<VT, CT>(value, o00 + W * MD + MD + c); atomicAdd(gacc + o00 + W * MD + MD + c, lh * lw * tgv); }
+          const int ca = pr.acc_permuted ? acc_pos(c, pr.D) : c;   // accumulator column (see acc_pos)
+          if (mask & 1) { d1 += top * load_as<VT, CT>(value, o00 + c); atomicAdd(gacc + o00 + ca, hh * hw * tgv); }
+          if (mask & 2) { d2 += top * load_as<VT, CT>(value, o00 + MD + c); atomicAdd(gacc + o00 + MD + ca, hh * lw * tgv); }
+          if (mask & 4) { d3 += top * load_as<VT, CT>(value, o00 + W * MD + c); atomicAdd(gacc + o00 + W * MD + ca, lh * hw * tgv); }
+          if (mask & 8) { d4 += top * load_as<VT, CT>(value, o00 + W * MD + MD + c); atomicAdd(gacc + o00 + W * MD + MD + ca, lh * lw * tgv); }
         }
         d1 = warp_sum(d1); d2 = warp_sum(d2); d3 = warp_sum(d3); d4 = warp_sum(d4);
       }

@@ -9,15 +9,15 @@ namespace msda {
 
 // vector kernels (fp32 / bf16 value, D in {16,32,64}, P in {4,8})
 bool fwd_vec_supported(int dtype, int D, int P, int L);
-int launch_forward_vec(const Problem &pr, int dtype, int grid, cudaStream_t stream);
-int launch_backward_vec(const Problem &pr, int dtype, int grid, cudaStream_t stream);
+int launch_forward_vec(const Problem &pr, int dtype, int grid, int min_blocks, cudaStream_t stream);
+int launch_backward_vec(const Problem &pr, int dtype, int grid, int min_blocks, cudaStream_t stream);
 
 // generic per-channel kernels (any D, P, L; fp32 / fp64 / bf16 value)
 int launch_forward_generic(const Problem &pr, int dtype, cudaStream_t stream);
 int launch_backward_generic(const Problem &pr, int dtype, cudaStream_t stream);
 
 // fp32 accumulator -> bf16 grad_value
-int launch_f32_to_bf16(const float *src, void *dst, long long n, cudaStream_t stream);
+int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, cudaStream_t stream);
 
 // deterministic backward (two-pass)
 size_t deterministic_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype);

@@ -75,7 +75,9 @@ class MSDeformAttn(nn.Module):
         bias = bias.expand(self.n_heads, self.n_levels, self.n_points, 2).reshape(-1)
         with torch.no_grad():
             self.sampling_offsets.weight.zero_()
-            self.sampling_offsets.bias = nn.Parameter(bias.clone())
+            # (the reference rebinds the bias to a fresh CPU tensor here; keeping device/dtype makes
+            # init_weights() safe to call after .cuda() as well)
+            self.sampling_offsets.bias = nn.Parameter(bias.to(self.sampling_offsets.weight).clone())
             self.attention_weights.weight.zero_()
             self.attention_weights.bias.zero_()
             nn.init.xavier_uniform_(self.value_proj.weight)

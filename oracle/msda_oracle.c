@@ -11,9 +11,13 @@
  *   backward  : ms_deform_im2col_cuda.cuh:87-159 (per-sample, per-channel gradient terms) and
  *               :301-403 (channel sums for grad_sampling_loc / grad_attn_weight are taken in
  *               ascending channel order, like the reference's lane-0 serial loop)
- *   geometry  : ms_deform_im2col_cuda.cuh:285-288 (coordinate + inside test; for fp32 the
- *               product loc*size is rounded to float and the "- 0.5" happens in double because
- *               0.5 is a double literal) and :38-41 (floor / low / high indices)
+ *   geometry  : ms_deform_im2col_cuda.cuh:285-288 (coordinate + inside test) and :38-41 (floor /
+ *               low / high indices).  The coordinate `loc * size - 0.5` is evaluated with ONE
+ *               rounding (fmaf / fma): that is what the reference computes as compiled by nvcc 12.9
+ *               for sm_100a -- every kernel of oracle/_ref/msda_ref_cuda.so holds
+ *               `FFMA R, loc, size, -0.5` (profiles/reference_sass_coordinate.txt) -- and it is
+ *               confirmed on the GPU by grad_sampling_loc parity with the reference op on samples
+ *               that sit on integer pixel coordinates (tests/test_gpu_vs_reference_cuda.py).
  *   layouts   : ms_deform_attn_cuda.cu:40-60 (value N,S,M,D; loc N,Lq,M,L,P,2 as (x,y);
  *               attn N,Lq,M,L,P; spatial_shapes (H,W) int64; level_start_index int64)
  *
@@ -38,11 +42,11 @@ typedef struct {
   double lh, lw;   /* fractional parts, held in the working precision's value set */
 } cell_t;
 
-/* fp32 path: float multiply, subtraction of a double 0.5, narrowing back to float. */
+/* fp32 path: single-rounded loc*size - 0.5 (see header). */
 static inline cell_t locate_f32(float loc_x, float loc_y, int H, int W) {
   cell_t c;
-  const float h_im = (float)((double)(loc_y * (float)H) - 0.5);
-  const float w_im = (float)((double)(loc_x * (float)W) - 0.5);
+  const float h_im = fmaf(loc_y, (float)H, -0.5f);
+  const float w_im = fmaf(loc_x, (float)W, -0.5f);
   c.inside = (h_im > -1.0f) && (w_im > -1.0f) && (h_im < (float)H) && (w_im < (float)W);
   c.h_low = 0; c.w_low = 0; c.lh = 0; c.lw = 0;
   if (c.inside) {
@@ -56,8 +60,8 @@ static inline cell_t locate_f32(float loc_x, float loc_y, int H, int W) {
 
 static inline cell_t locate_f64(double loc_x, double loc_y, int H, int W) {
   cell_t c;
-  const double h_im = loc_y * (double)H - 0.5;
-  const double w_im = loc_x * (double)W - 0.5;
+  const double h_im = fma(loc_y, (double)H, -0.5);
+  const double w_im = fma(loc_x, (double)W, -0.5);
   c.inside = (h_im > -1.0) && (w_im > -1.0) && (h_im < (double)H) && (w_im < (double)W);
   c.h_low = 0; c.w_low = 0; c.lh = 0; c.lw = 0;
   if (c.inside) {

@@ -127,11 +127,18 @@ def test_level_counts(L):
 
 @pytest.mark.parametrize("N,dist", [(1, "U"), (1, "I"), (2, "W")])
 def test_full_size_swin_t_vs_oracle(N, dist):
-    """BASELINE.json configs[0] shape (800x1333 pyramid, 22,223 queries, 8 heads x 32, 4 x 4 samples)."""
+    """BASELINE.json configs[0] shape (800x1333 pyramid, 22,223 queries, 8 heads x 32, 4 x 4 samples).
+    Strict 1e-5 against the fp32 oracle (same arithmetic contract as the reference CUDA op); against fp64
+    truth the bound is 2e-5 because fp32 pixel coordinates at W=167 alone cost ~1e-5 -- the reference CUDA
+    op measured on the same inputs sits at 1.02e-5 from truth (profiles/r01_parity_notes.md)."""
     g = make_inputs(SWIN_T_800x1333, N=N, M=8, D=32, Lq=None, P=4, dist=dist, seed=3)
-    truth_out = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
-    truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
-    check_all(g, run_cuda(g, torch.float32), truth, FP32_TOL, gl_tol=2e-5)
+    args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
+    res = run_cuda(g, torch.float32)
+    o32 = (oracle.forward(*args, np.float32),) + oracle.backward(*args, g["grad_out"], np.float32)
+    for name, got, want in zip(("output", "grad_value", "grad_sampling_loc", "grad_attn_weight"), res, o32):
+        assert_close(name + " vs fp32 oracle", got.reshape(want.shape), want, FP32_TOL)
+    truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
+    check_all(g, res, truth, 2e-5, gl_tol=4e-5)
 
 
 def test_full_size_decoder_bf16_vs_oracle():

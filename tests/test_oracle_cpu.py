@@ -62,20 +62,25 @@ def test_reference_testpy_tolerances():
     assert np.allclose(out32, g["out_f32"], rtol=1e-2, atol=1e-3)
 
 
-def test_fp32_coordinate_is_mul_then_sub():
-    """cuh:285-286: float product rounded, then '- 0.5' in double, narrowed to float.  That equals
-    float(fl(loc*size) - 0.5f) for every input (the double subtraction is exact or rounds the same
-    way), which is what the CUDA kernels compute with __fmul_rn/__fsub_rn; an fma would differ."""
+def test_fp32_coordinate_is_single_rounded():
+    """The reference AS COMPILED contracts `loc * size - 0.5` (cuh:285-286) into one FFMA
+    (profiles/reference_sass_coordinate.txt), so the oracle's integer records must equal a float64
+    evaluation rounded once -- and must NOT equal the unfused multiply-then-subtract, which differs in
+    a measurable share of coordinates and flips floor() for some samples on the pixel lattice."""
     rng = np.random.default_rng(0)
-    loc = rng.random(200000, dtype=np.float32) * 1.5 - 0.25
-    for size in (167, 100, 84, 13, 1):
-        prod = (loc * np.float32(size)).astype(np.float32)
-        via_double = (prod.astype(np.float64) - 0.5).astype(np.float32)
-        via_float = (prod - np.float32(0.5)).astype(np.float32)
-        assert np.array_equal(via_double, via_float)
-        fused = (loc.astype(np.float64) * size - 0.5).astype(np.float32)
-        if size == 167:
-            assert (fused != via_float).mean() > 0.005     # the naive contraction is NOT bit-exact
+    n = 100000
+    loc = (rng.random((1, n, 1, 1, 1, 2), dtype=np.float32) * 1.5 - 0.25).astype(np.float32)
+    loc[0, :1000, 0, 0, 0, 1] = (np.arange(1000, dtype=np.float32) % 100 + 0.5) / np.float32(100)   # pixel centres
+    shapes = np.array([[100, 167]], dtype=np.int64)
+    rec = oracle.sample_index(shapes, np.zeros(1, np.int64), loc, 100 * 167)[0, :, 0, 0, 0]
+    h = (loc[0, :, 0, 0, 0, 1].astype(np.float64) * 100 - 0.5).astype(np.float32)     # one rounding
+    w = (loc[0, :, 0, 0, 0, 0].astype(np.float64) * 167 - 0.5).astype(np.float32)
+    inside = (h > -1) & (w > -1) & (h < 100) & (w < 167)
+    assert np.array_equal(rec[:, 2] & 1, inside.astype(np.int32))
+    assert np.array_equal(rec[inside, 0], np.floor(h[inside]).astype(np.int32))
+    assert np.array_equal(rec[inside, 1], np.floor(w[inside]).astype(np.int32))
+    unfused = (loc[0, :, 0, 0, 0, 0] * np.float32(167)).astype(np.float32) - np.float32(0.5)
+    assert (unfused != w).mean() > 0.005
 
 
 def test_sample_index_records():
