@@ -279,12 +279,10 @@ def run_ours(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from msda_b200 import dist_utils
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dist_utils.max_over_ranks(x, device)
 
     layers = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, args.dist, 100 + l, device), args.variant)
               for l in range(cfg["layers"])]

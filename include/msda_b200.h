@@ -51,7 +51,7 @@ enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2 };
 /* backward accumulation mode for grad_value */
 enum {
   MSDA_BWD_ATOMIC = 0,        /* vector red.global.add into fp32 (order not reproducible)        */
-  MSDA_BWD_DETERMINISTIC = 1  /* two-pass: bucket samples by destination, then ordered gather-sum */
+  MSDA_BWD_DETERMINISTIC = 1  /* two-pass: max|grad| -> scale, then 64-bit fixed-point integer atomics */
 };
 
 enum {

@@ -102,10 +102,8 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
 
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
   if (check_dims(N, S, M, D, L, Lq, P, dtype) != MSDA_OK) return 0;
-  size_t bytes = 0;
-  if (dtype == MSDA_BF16) bytes += (size_t)N * S * M * D * sizeof(float);   // fp32 accumulator
-  if (mode == MSDA_BWD_DETERMINISTIC) bytes += deterministic_workspace_bytes(N, S, M, D, L, Lq, P, dtype);
-  return bytes;
+  if (mode == MSDA_BWD_DETERMINISTIC) return deterministic_workspace_bytes(N, S, M, D, L, Lq, P, dtype);
+  return dtype == MSDA_BF16 ? (size_t)N * S * M * D * sizeof(float) : 0;   // fp32 accumulator for bf16
 }
 
 int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,

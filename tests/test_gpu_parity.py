@@ -176,3 +176,28 @@ def test_full_size_properties_bs4():
     assert abs((attn.double() * ga.double()).sum().item() - lhs) <= 1e-4 * (o1.double().abs() * gout.double().abs()).sum().item()
     # idempotence / run-to-run: forward is bit-reproducible
     assert torch.equal(o1, f(v1))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+def test_deterministic_mode_is_bit_reproducible_and_accurate(dtype):
+    """MSDA_BWD_DETERMINISTIC: identical bits run to run, and the same numbers as the atomic mode."""
+    g = make_inputs(ENC_SMALL, N=2, M=8, D=32, Lq=None, P=4, dist="I", seed=6)   # heavy write conflicts
+    if dtype == torch.bfloat16:
+        g["value"] = oracle.bf16_round(g["value"]); g["grad_out"] = oracle.bf16_round(g["grad_out"])
+    runs = [run_cuda(g, dtype, mode=1) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0], r):
+            assert np.array_equal(a, b)
+    truth_out = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
+    truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
+    tol = {torch.float32: FP32_TOL, torch.bfloat16: BF16_TOL, torch.float64: 1e-12}[dtype]
+    check_all(g, runs[0], truth, tol, gl_tol=max(tol, 1e-10), mask_tol=1e-4 if dtype != torch.float64 else 1e-9)
+
+
+def test_deterministic_mode_full_size():
+    g = make_inputs(SWIN_T_800x1333, N=1, M=8, D=32, Lq=None, P=4, dist="U", seed=12)
+    a = run_cuda(g, torch.float32, mode=1)
+    b = run_cuda(g, torch.float32, mode=1)
+    assert np.array_equal(a[1], b[1])
+    atomic = run_cuda(g, torch.float32, mode=0)
+    assert oracle.normwise(a[1], atomic[1]) < 1e-6
