@@ -68,7 +68,7 @@ const char *msda_error_string(int code);
 /* Variant selector for experiments and A/B profiling; 0 = the library's default choice.
  * bit 0..3  : kernel family (1 = generic per-channel kernels, 2 = vector kernels, linear order,
  *             3 = vector kernels, query-tile order)
- * bit 4..5  : CTAs/SM the vector kernels are register-limited for (0: 2, 1: 3, 2: 4)
+ * bit 4..5  : CTAs/SM the vector kernels are register-limited for (0: default, 1: 2, 2: 3, 3: 4)
  * bit 8      : (backward, atomic mode) MSDA_VARIANT_NO_ZERO   -- the caller has already zeroed the
  *             accumulator (grad_value, or the workspace for bf16); skip the memset
  * bit 9      : (backward, bf16)         MSDA_VARIANT_NO_NARROW -- leave the fp32 accumulator in the
@@ -118,6 +118,16 @@ size_t msda_host_d2h_bytes(const msda_host_ctx *ctx);
 /* All pointers are HOST memory (pinned for full speed).  Copies inputs to the device, runs forward
  * and backward, copies the four results back, and returns after the stream has drained. */
 int msda_host_fwd_bwd(msda_host_ctx *ctx, const void *value, const int64_t *spatial_shapes,
+                      const int64_t *level_start_index, const void *sampling_loc,
+                      const void *attn_weight, const void *grad_output, void *output,
+                      void *grad_value, void *grad_sampling_loc, void *grad_attn_weight);
+/* The same, split: msda_host_submit() enqueues the H2D copies, both kernels and the D2H copies on the
+ * context's own three streams and returns at once; msda_host_wait() blocks until the results are in the
+ * host buffers.  One submission per context at a time; with several contexts in flight the copies of one
+ * overlap the kernels and the opposite-direction copies of the others.  Host buffers must be left alone
+ * between submit and wait. */
+int msda_host_wait(msda_host_ctx *ctx);
+int msda_host_submit(msda_host_ctx *ctx, const void *value, const int64_t *spatial_shapes,
                       const int64_t *level_start_index, const void *sampling_loc,
                       const void *attn_weight, const void *grad_output, void *output,
                       void *grad_value, void *grad_sampling_loc, void *grad_attn_weight);

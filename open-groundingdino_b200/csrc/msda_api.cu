@@ -50,8 +50,13 @@ int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool
 // width allows it; a function of (dtype, D) only, so every kernel family and the narrowing agree.
 bool acc_is_permuted(int dtype, int D) { return dtype == MSDA_BF16 && D % 8 == 0; }
 
-// variant bits 4..5: CTAs per SM the vector kernels are compiled for (0 -> 2, 1 -> 3, 2 -> 4)
-int min_blocks(int variant) { return 2 + ((variant >> 4) & 3) > 4 ? 4 : 2 + ((variant >> 4) & 3); }
+// variant bits 4..5: CTAs per SM the vector kernels are compiled for (1 -> 2, 2 -> 3, 3 -> 4); 0 picks the
+// measured best: 3 for the forward (gather-latency bound, profits from 24 resident warps), 2 for the
+// backward (bound by the L2 atomic units; more warps in flight only add contention) -- tools/sweep.py.
+int min_blocks(int variant, int dflt) {
+  const int sel = (variant >> 4) & 3;
+  return sel == 0 ? dflt : sel + 1;
+}
 
 int vec_grid(const Problem &pr, int resident_per_sm) {
   // Persistent CTAs: exactly as many as stay resident (the kernels are register-limited to
@@ -97,7 +102,7 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
   const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
   if (family == 1) return launch_forward_generic(pr, dtype, stream);
   pr.tiled = (family == 3);
-  return launch_forward_vec(pr, dtype, vec_grid(pr, min_blocks(variant)), min_blocks(variant), stream);
+  return launch_forward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 3)), min_blocks(variant, 3), stream);
 }
 
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
@@ -150,7 +155,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     rc = launch_backward_generic(pr, dtype, stream);
   } else {
     pr.tiled = (family == 3);
-    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant)), min_blocks(variant), stream);
+    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), min_blocks(variant, 2), stream);
   }
   if (rc != MSDA_OK) return rc;
   if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW))
@@ -176,21 +181,31 @@ int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_
 }
 
 // ---- host-buffer path ---------------------------------------------------------------------------
+// One context = device buffers for one problem size + three streams (H2D, kernels, D2H) chained by events,
+// so several contexts in flight overlap their copies in both PCIe directions with each other's kernels.
 struct msda_host_ctx {
   int N, S, M, D, L, Lq, P, dtype, mode;
   size_t b_value, b_loc, b_attn, b_out, b_shapes, b_starts, b_ws;
   char *d_value, *d_loc, *d_attn, *d_gout, *d_out, *d_gvalue, *d_gloc, *d_gattn, *d_ws;
   int64_t *d_shapes, *d_starts;
-  cudaStream_t stream;
+  cudaStream_t s_in, s_k, s_out;
+  cudaEvent_t e_in, e_fwd, e_bwd, e_done, e_free;
+  bool in_flight;
 };
 
 void msda_host_destroy(msda_host_ctx *c) {
   if (!c) return;
+  if (c->in_flight && c->e_done) cudaEventSynchronize(c->e_done);
   void *ptrs[] = {c->d_value, c->d_loc, c->d_attn, c->d_gout, c->d_out, c->d_gvalue,
                   c->d_gloc, c->d_gattn, c->d_ws, c->d_shapes, c->d_starts};
   for (void *p : ptrs)
     if (p) cudaFree(p);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaStream_t streams[] = {c->s_in, c->s_k, c->s_out};
+  for (cudaStream_t st : streams)
+    if (st) cudaStreamDestroy(st);
+  cudaEvent_t events[] = {c->e_in, c->e_fwd, c->e_bwd, c->e_done, c->e_free};
+  for (cudaEvent_t ev : events)
+    if (ev) cudaEventDestroy(ev);
   delete c;
 }
 
@@ -207,7 +222,13 @@ int msda_host_create(msda_host_ctx **out, int N, int S, int M, int D, int L, int
   c->b_shapes = (size_t)L * 2 * sizeof(int64_t);
   c->b_starts = (size_t)L * sizeof(int64_t);
   c->b_ws = msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dtype, mode);
-  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaSuccess;
+  cudaStream_t *streams[] = {&c->s_in, &c->s_k, &c->s_out};
+  for (cudaStream_t *st : streams)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+  cudaEvent_t *events[] = {&c->e_in, &c->e_fwd, &c->e_bwd, &c->e_done, &c->e_free};
+  for (cudaEvent_t *ev : events)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   auto alloc = [&](char **p, size_t bytes) {
     if (e == cudaSuccess && bytes > 0) e = cudaMalloc(reinterpret_cast<void **>(p), bytes);
   };
@@ -229,36 +250,62 @@ size_t msda_host_h2d_bytes(const msda_host_ctx *c) {
 }
 size_t msda_host_d2h_bytes(const msda_host_ctx *c) { return c ? c->b_out + c->b_value + c->b_loc + c->b_attn : 0; }
 
+int msda_host_submit(msda_host_ctx *c, const void *value, const int64_t *spatial_shapes,
+                     const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                     const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                     void *grad_attn_weight) {
+  if (!c || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
+      !output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
+    return MSDA_E_INVALID;
+  if (c->in_flight) return MSDA_E_INVALID;   // one submission per context at a time: wait first
+  cudaError_t e;
+#define MSDA_TRY(x) if ((e = (x)) != cudaSuccess) return (int)e
+  // inputs (the previous use of the device input buffers ended with the previous wait)
+  MSDA_TRY(cudaMemcpyAsync(c->d_shapes, spatial_shapes, c->b_shapes, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaMemcpyAsync(c->d_starts, level_start_index, c->b_starts, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaMemcpyAsync(c->d_value, value, c->b_value, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaMemcpyAsync(c->d_loc, sampling_loc, c->b_loc, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaMemcpyAsync(c->d_attn, attn_weight, c->b_attn, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaMemcpyAsync(c->d_gout, grad_output, c->b_out, cudaMemcpyHostToDevice, c->s_in));
+  MSDA_TRY(cudaEventRecord(c->e_in, c->s_in));
+  // kernels
+  MSDA_TRY(cudaStreamWaitEvent(c->s_k, c->e_in, 0));
+  int rc = msda_forward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_out, c->N, c->S, c->M,
+                        c->D, c->L, c->Lq, c->P, c->dtype, 0, c->s_k);
+  if (rc != MSDA_OK) return rc;
+  MSDA_TRY(cudaEventRecord(c->e_fwd, c->s_k));
+  rc = msda_backward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_gout, c->d_gvalue,
+                     c->d_gloc, c->d_gattn, c->N, c->S, c->M, c->D, c->L, c->Lq, c->P, c->dtype, c->mode, 0,
+                     c->d_ws, c->b_ws, c->s_k);
+  if (rc != MSDA_OK) return rc;
+  MSDA_TRY(cudaEventRecord(c->e_bwd, c->s_k));
+  // results: the output leaves while the backward runs
+  MSDA_TRY(cudaStreamWaitEvent(c->s_out, c->e_fwd, 0));
+  MSDA_TRY(cudaMemcpyAsync(output, c->d_out, c->b_out, cudaMemcpyDeviceToHost, c->s_out));
+  MSDA_TRY(cudaStreamWaitEvent(c->s_out, c->e_bwd, 0));
+  MSDA_TRY(cudaMemcpyAsync(grad_value, c->d_gvalue, c->b_value, cudaMemcpyDeviceToHost, c->s_out));
+  MSDA_TRY(cudaMemcpyAsync(grad_sampling_loc, c->d_gloc, c->b_loc, cudaMemcpyDeviceToHost, c->s_out));
+  MSDA_TRY(cudaMemcpyAsync(grad_attn_weight, c->d_gattn, c->b_attn, cudaMemcpyDeviceToHost, c->s_out));
+  MSDA_TRY(cudaEventRecord(c->e_done, c->s_out));
+#undef MSDA_TRY
+  c->in_flight = true;
+  return MSDA_OK;
+}
+
+int msda_host_wait(msda_host_ctx *c) {
+  if (!c) return MSDA_E_INVALID;
+  if (!c->in_flight) return MSDA_OK;
+  c->in_flight = false;
+  return (int)cudaEventSynchronize(c->e_done);
+}
+
 int msda_host_fwd_bwd(msda_host_ctx *c, const void *value, const int64_t *spatial_shapes,
                       const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
                       const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
                       void *grad_attn_weight) {
-  if (!c || !value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
-      !output || !grad_value || !grad_sampling_loc || !grad_attn_weight)
-    return MSDA_E_INVALID;
-  cudaStream_t s = c->stream;
-  cudaError_t e;
-#define MSDA_TRY(x) if ((e = (x)) != cudaSuccess) return (int)e
-  MSDA_TRY(cudaMemcpyAsync(c->d_shapes, spatial_shapes, c->b_shapes, cudaMemcpyHostToDevice, s));
-  MSDA_TRY(cudaMemcpyAsync(c->d_starts, level_start_index, c->b_starts, cudaMemcpyHostToDevice, s));
-  MSDA_TRY(cudaMemcpyAsync(c->d_value, value, c->b_value, cudaMemcpyHostToDevice, s));
-  MSDA_TRY(cudaMemcpyAsync(c->d_loc, sampling_loc, c->b_loc, cudaMemcpyHostToDevice, s));
-  MSDA_TRY(cudaMemcpyAsync(c->d_attn, attn_weight, c->b_attn, cudaMemcpyHostToDevice, s));
-  MSDA_TRY(cudaMemcpyAsync(c->d_gout, grad_output, c->b_out, cudaMemcpyHostToDevice, s));
-  int rc = msda_forward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_out, c->N, c->S, c->M,
-                        c->D, c->L, c->Lq, c->P, c->dtype, 0, s);
-  if (rc != MSDA_OK) return rc;
-  MSDA_TRY(cudaMemcpyAsync(output, c->d_out, c->b_out, cudaMemcpyDeviceToHost, s));
-  rc = msda_backward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_gout, c->d_gvalue,
-                     c->d_gloc, c->d_gattn, c->N, c->S, c->M, c->D, c->L, c->Lq, c->P, c->dtype, c->mode, 0,
-                     c->d_ws, c->b_ws, s);
-  if (rc != MSDA_OK) return rc;
-  MSDA_TRY(cudaMemcpyAsync(grad_value, c->d_gvalue, c->b_value, cudaMemcpyDeviceToHost, s));
-  MSDA_TRY(cudaMemcpyAsync(grad_sampling_loc, c->d_gloc, c->b_loc, cudaMemcpyDeviceToHost, s));
-  MSDA_TRY(cudaMemcpyAsync(grad_attn_weight, c->d_gattn, c->b_attn, cudaMemcpyDeviceToHost, s));
-  MSDA_TRY(cudaStreamSynchronize(s));
-#undef MSDA_TRY
-  return MSDA_OK;
+  const int rc = msda_host_submit(c, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                  output, grad_value, grad_sampling_loc, grad_attn_weight);
+  return rc != MSDA_OK ? rc : msda_host_wait(c);
 }
 
 }  // extern "C"

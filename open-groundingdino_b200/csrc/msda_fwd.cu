@@ -20,7 +20,8 @@
 
 namespace msda {
 
-template <typename VT, int D, int P, int MINB>
+// PB = points whose 4 gathers are in flight together (register staging: PB*16 registers)
+template <typename VT, int D, int P, int MINB, int PB>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
   constexpr int NP = Chan<VT>::kPairs;     // fp32x2 accumulators per lane
@@ -81,33 +82,37 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
         const int WMD = W * MD;
 
-        uint4 raw[P][4];
-        float wt[P][4];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
-          const bool in = act && c.inside;
-          const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          const float aw = in ? a[p] : 0.f;
-          const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
-          const float hh = 1.f - lh, hw = 1.f - lw;
-          const float ah = hh * aw, al = lh * aw;
-          wt[p][0] = ah * hw; wt[p][1] = ah * lw; wt[p][2] = al * hw; wt[p][3] = al * lw;
-          const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
-          raw[p][0] = gather16(p00, mask & 1);
-          raw[p][1] = gather16(p00 + MD, mask & 2);
-          raw[p][2] = gather16(p00 + WMD, mask & 4);
-          raw[p][3] = gather16(p00 + WMD + MD, mask & 8);
-        }
+        for (int p0 = 0; p0 < P; p0 += PB) {
+          uint4 raw[PB][4];
+          float wt[PB][4];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
+          for (int pp = 0; pp < PB; ++pp) {
+            const int p = p0 + pp;
+            const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+            const bool in = act && c.inside;
+            const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+            const float aw = in ? a[p] : 0.f;
+            const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float ah = hh * aw, al = lh * aw;
+            wt[pp][0] = ah * hw; wt[pp][1] = ah * lw; wt[pp][2] = al * hw; wt[pp][3] = al * lw;
+            const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
+            raw[pp][0] = gather16(p00, mask & 1);
+            raw[pp][1] = gather16(p00 + MD, mask & 2);
+            raw[pp][2] = gather16(p00 + WMD, mask & 4);
+            raw[pp][3] = gather16(p00 + WMD + MD, mask & 8);
+          }
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            unsigned long long v[NP];
-            Chan<VT>::unpack2(raw[p][kk], v);
-            const unsigned long long w2 = pack_f2(wt[p][kk], wt[p][kk]);
+          for (int pp = 0; pp < PB; ++pp) {
 #pragma unroll
-            for (int c = 0; c < NP; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
+            for (int kk = 0; kk < 4; ++kk) {
+              unsigned long long v[NP];
+              Chan<VT>::unpack2(raw[pp][kk], v);
+              const unsigned long long w2 = pack_f2(wt[pp][kk], wt[pp][kk]);
+#pragma unroll
+              for (int c = 0; c < NP; ++c) acc[c] = ffma2(w2, v[c], acc[c]);
+            }
           }
         }
       }
@@ -129,9 +134,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
 
 template <typename VT, int D, int P>
 static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
-  if (minb == 4) fwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
-  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
-  else fwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+  if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
+  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, 2><<<grid, kThreads, 0, stream>>>(pr);
+  else fwd_vec_kernel<VT, D, P, 2, 4><<<grid, kThreads, 0, stream>>>(pr);
   return (int)cudaGetLastError();
 }
 

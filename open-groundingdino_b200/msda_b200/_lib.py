@@ -20,7 +20,7 @@ VARIANT_NO_ZERO, VARIANT_NO_NARROW = 0x100, 0x200
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
     "msda_backward_finish_bf16", "msda_sample_index", "msda_host_create", "msda_host_destroy", "msda_host_h2d_bytes", "msda_host_d2h_bytes",
-    "msda_host_fwd_bwd",
+    "msda_host_fwd_bwd", "msda_host_submit", "msda_host_wait",
 )
 
 _lib = None
@@ -55,6 +55,10 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_host_d2h_bytes.argtypes = [vp]
     lib.msda_host_fwd_bwd.restype = i
     lib.msda_host_fwd_bwd.argtypes = [vp] * 11
+    lib.msda_host_submit.restype = i
+    lib.msda_host_submit.argtypes = [vp] * 11
+    lib.msda_host_wait.restype = i
+    lib.msda_host_wait.argtypes = [vp]
 
 
 def lib() -> ctypes.CDLL:

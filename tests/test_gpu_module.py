@@ -165,3 +165,28 @@ def test_host_buffer_abi_path():
     want = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
     wgv, wgl, wga = oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
     assert oracle.normwise(out, want) < 1e-5 and oracle.normwise(gv, wgv) < 1e-5 and oracle.normwise(ga, wga) < 1e-5
+
+
+def test_host_submit_wait_pipeline():
+    """Several contexts in flight: results equal the synchronous call's."""
+    from msda_b200 import _lib
+    lib = _lib.lib()
+    gs = [make_inputs(SHAPES, N=1, M=8, D=32, Lq=60, P=4, dist="W", seed=20 + k) for k in range(3)]
+    N, S, M, D, L, Lq, P = gs[0]["dims"]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ctxs, outs = [], []
+    for g in gs:
+        c = ctypes.c_void_p()
+        _lib.check(lib.msda_host_create(ctypes.byref(c), N, S, M, D, L, Lq, P, _lib.MSDA_F32, 0), "create")
+        o = (np.empty((N, Lq, M * D), np.float32), np.empty_like(g["value"]), np.empty_like(g["loc"]), np.empty_like(g["attn"]))
+        _lib.check(lib.msda_host_submit(c, p(g["value"]), p(g["shapes"]), p(g["starts"]), p(g["loc"]), p(g["attn"]),
+                                        p(g["grad_out"]), p(o[0]), p(o[1]), p(o[2]), p(o[3])), "submit")
+        ctxs.append(c); outs.append(o)
+    assert lib.msda_host_submit(ctxs[0], *([p(gs[0]["value"])] * 10)) == -1      # busy context is refused
+    for c in ctxs:
+        _lib.check(lib.msda_host_wait(c), "wait")
+    for g, o, c in zip(gs, outs, ctxs):
+        want = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
+        wgv = oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)[0]
+        assert oracle.normwise(o[0], want) < 1e-5 and oracle.normwise(o[1], wgv) < 1e-5
+        lib.msda_host_destroy(c)

@@ -200,4 +200,4 @@ def test_deterministic_mode_full_size():
     b = run_cuda(g, torch.float32, mode=1)
     assert np.array_equal(a[1], b[1])
     atomic = run_cuda(g, torch.float32, mode=0)
-    assert oracle.normwise(a[1], atomic[1]) < 1e-6
+    assert oracle.normwise(a[1], atomic[1]) < 1e-5     # the atomic mode's own fp32 summation noise
