@@ -155,7 +155,8 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     rc = launch_backward_generic(pr, dtype, stream);
   } else {
     pr.tiled = (family == 3);
-    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), min_blocks(variant, 2), stream);
+    const int abl = (variant >> 6) & 3;   // profiling ablations, see msda_bwd.cu
+    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
   }
   if (rc != MSDA_OK) return rc;
   if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW))

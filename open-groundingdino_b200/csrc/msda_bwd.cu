@@ -47,7 +47,8 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
   }
 }
 
-template <typename VT, int D, int P, int MINB>
+// ABL: ablation for profiling only (0 = the real kernel, 1 = reductions suppressed, 2 = value gathers suppressed)
+template <typename VT, int D, int P, int MINB, int ABL = 0>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;
   constexpr int NP = Chan<VT>::kPairs;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const int off = pend_off + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
-            if (((pend_mask >> kk) & 1) && pend[kk] != 0.f) {
+            if (ABL != 1 && ((pend_mask >> kk) & 1) && pend[kk] != 0.f) {
               const unsigned long long c2 = pack_f2(pend[kk], pend[kk]);
 #pragma unroll
               for (int h4 = 0; h4 < NP / 2; ++h4) {
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             const bool on = (mask >> kk) & 1;
             const int off = o00 + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
             unsigned long long v[NP];
-            Chan<VT>::unpack2(gather16(slab + off, on), v);
+            Chan<VT>::unpack2(gather16(slab + off, on && ABL != 2), v);
             unsigned long long dot2 = 0ull;
 #pragma unroll
             for (int cidx = 0; cidx < NP; ++cidx) dot2 = ffma2(go[cidx], v[cidx], dot2);
@@ -241,6 +242,11 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
 template <typename VT, int D, int P>
 static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
+  if (D == 32 && P == 4 && minb >= 100) {   // profiling ablations (variant bits 6..7), D=32/P=4 only
+    if (minb == 101) bwd_vec_kernel<VT, 32, 4, 2, 1><<<grid, kThreads, 0, stream>>>(pr);
+    else bwd_vec_kernel<VT, 32, 4, 2, 2><<<grid, kThreads, 0, stream>>>(pr);
+    return (int)cudaGetLastError();
+  }
   if (minb == 4) bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
   else if (minb == 3) bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
   else bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
