@@ -256,7 +256,7 @@ def run_reference_arm(args, cfg):
             "config": {"workload": cfg["text"], "sample_per_step": desc},
             "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, cfg):
@@ -420,7 +420,7 @@ def run_ours(args, cfg):
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
                 "clocks": clocks.summary(), "ms_fwd_per_layer": fwd_kernel_ms, "ms_bwd_kernel_per_layer": bwd_kernel_ms}
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -467,7 +467,27 @@ def time_reference_cuda(torch, layers, cfg, ours_ms_step):
     return {"ms_per_step": ms, "speedup_ours": ms / ours_ms_step, "note": "same GPU, same tensors, fp32 op" + (" + casts" if bf16 else "")}
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Route fd 1 to stderr for the whole run (NCCL and friends print banners on stdout at C level) and keep
+    the real stdout for the ONE JSON line the driver parses."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
