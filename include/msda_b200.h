@@ -99,6 +99,31 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 int msda_backward_finish_bf16(const void *workspace, void *grad_value, int batch, int spatial_size,
                               int num_heads, int channels, void *stream);
 
+/* ---- fused pre-op (next row f1 of the scope table) --------------------------------------------------
+ * MSDeformAttn.forward computes attention_weights = softmax(logits over L*P) and sampling_locations =
+ * ref + offsets / (W,H)  (or  ref_xy + offsets / P * ref_wh * 0.5 for 4-d references) with elementwise
+ * PyTorch kernels before calling the op (ops/modules/ms_deform_attn.py:98-108).  These entry points take the
+ * raw linear-layer outputs instead and do that arithmetic in the kernel prologue (and its transpose in the
+ * backward epilogue), so neither tensor round-trips through HBM:
+ *   sampling_offsets  (N, Lq, M, L, P, 2)  q_dtype (MSDA_F32 or MSDA_BF16)
+ *   attn_logits       (N, Lq, M, L*P)      q_dtype
+ *   reference_points  (N, Lq, L, ref_dim)  fp32, ref_dim = 2 or 4 (no gradient is produced for them)
+ * grad_offsets / grad_logits have the shapes and dtype of their inputs.  Atomic backward mode only.
+ * msda_fused_supported() tells whether this build has a fused kernel for a head width / level count /
+ * point count / dtype pair (D = 32, P = 4); otherwise callers use msda_forward/msda_backward. */
+int msda_fused_supported(int channels, int num_levels, int num_point, int value_dtype, int q_dtype);
+int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_offsets, const void *attn_logits, const float *reference_points,
+                       void *output, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                       int num_query, int num_point, int ref_dim, int value_dtype, int q_dtype, int variant,
+                       void *stream);
+int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_offsets, const void *attn_logits, const float *reference_points,
+                        const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits,
+                        int batch, int spatial_size, int num_heads, int channels, int num_levels, int num_query,
+                        int num_point, int ref_dim, int value_dtype, int q_dtype, int variant, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
 /* rec: int32 (N, Lq, M, L, P, 4) = [h_low, w_low, flags, slab_row]; flags bit0 = sample accepted,
  * bits1..4 = which of the 4 neighbours exist; slab_row = b*S + level_start_index[l].  fp32 path. */
 int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index,

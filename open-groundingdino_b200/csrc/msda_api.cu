@@ -164,6 +164,71 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
   return rc;
 }
 
+// ---- fused pre-op entry points --------------------------------------------
+int msda_fused_supported(int D, int L, int P, int value_dtype, int q_dtype) {
+  if (D != 32 || P != 4 || L < 1) return 0;
+  if (value_dtype == MSDA_F32) return (q_dtype == MSDA_F32 && L <= 4) ? 1 : 0;       // 4 level groups per warp
+  if (value_dtype == MSDA_BF16) return ((q_dtype == MSDA_F32 || q_dtype == MSDA_BF16) && L <= 8) ? 1 : 0;
+  return 0;
+}
+
+int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_offsets, const void *attn_logits, const float *reference_points,
+                       void *output, int N, int S, int M, int D, int L, int Lq, int P, int ref_dim, int dtype,
+                       int q_dtype, int variant, void *stream_) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points || !output)
+    return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (ref_dim != 2 && ref_dim != 4) return MSDA_E_INVALID;
+  if (!msda_fused_supported(D, L, P, dtype, q_dtype)) return MSDA_E_UNSUPPORTED;
+  if (!(aligned16(value) && aligned16(sampling_offsets) && aligned16(attn_logits) && aligned16(reference_points) &&
+        aligned16(output)))
+    return MSDA_E_UNSUPPORTED;
+  Problem pr{};
+  pr.value = value; pr.shapes = spatial_shapes; pr.starts = level_start_index;
+  pr.loc = sampling_offsets; pr.attn = attn_logits; pr.ref = reference_points; pr.ref_dim = ref_dim; pr.out = output;
+  pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.tile_w_log2 = 3;
+  pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
+  return launch_forward_vec(pr, dtype, vec_grid(pr, 3), q_dtype == MSDA_BF16 ? 202 : 201, static_cast<cudaStream_t>(stream_));
+}
+
+int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_offsets, const void *attn_logits, const float *reference_points,
+                        const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits, int N, int S,
+                        int M, int D, int L, int Lq, int P, int ref_dim, int dtype, int q_dtype, int variant,
+                        void *workspace, size_t workspace_bytes, void *stream_) {
+  if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
+      !grad_output || !grad_value || !grad_offsets || !grad_logits)
+    return MSDA_E_INVALID;
+  if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (ref_dim != 2 && ref_dim != 4) return MSDA_E_INVALID;
+  if (!msda_fused_supported(D, L, P, dtype, q_dtype)) return MSDA_E_UNSUPPORTED;
+  const size_t need = msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dtype, MSDA_BWD_ATOMIC);
+  if (need > 0 && (!workspace || workspace_bytes < need)) return MSDA_E_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Problem pr{};
+  pr.value = value; pr.shapes = spatial_shapes; pr.starts = level_start_index;
+  pr.loc = sampling_offsets; pr.attn = attn_logits; pr.ref = reference_points; pr.ref_dim = ref_dim;
+  pr.grad_out = grad_output; pr.grad_loc = grad_offsets; pr.grad_attn = grad_logits;
+  pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.tile_w_log2 = 3;
+  pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
+  void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
+  pr.acc_permuted = acc_is_permuted(dtype, D);
+  pr.grad_value_acc = acc;
+  if (!(aligned16(value) && aligned16(sampling_offsets) && aligned16(attn_logits) && aligned16(reference_points) &&
+        aligned16(grad_output) && aligned16(acc)))
+    return MSDA_E_UNSUPPORTED;
+  const size_t n_value = (size_t)N * S * M * D;
+  if (cudaError_t e = cudaMemsetAsync(acc, 0, n_value * 4, stream)) return (int)e;
+  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), q_dtype == MSDA_BF16 ? 202 : 201, stream);
+  if (rc != MSDA_OK) return rc;
+  if (dtype == MSDA_BF16)
+    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0, stream);
+  return rc;
+}
+
 int msda_backward_finish_bf16(const void *workspace, void *grad_value, int N, int S, int M, int D, void *stream_) {
   if (!workspace || !grad_value || N <= 0 || S <= 0 || M <= 0 || D <= 0) return MSDA_E_INVALID;
   return launch_f32_to_bf16(static_cast<const float *>(workspace), grad_value, (long long)N * S * M * D, D,

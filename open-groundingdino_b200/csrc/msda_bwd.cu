@@ -22,6 +22,7 @@
 // add); for bf16 the accumulator is a workspace that msda_api.cu narrows once at the end.
 #include "msda_common.cuh"
 #include "msda_launch.h"
+#include "msda_pre.cuh"
 
 namespace msda {
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 }
 
 // ABL: ablation for profiling only (0 = the real kernel, 1 = reductions suppressed, 2 = value gathers suppressed)
-template <typename VT, int D, int P, int MINB, int ABL = 0>
+template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;
   constexpr int NP = Chan<VT>::kPairs;
@@ -67,15 +68,10 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   const int rounds = (pr.L + GI - 1) / GI;
   const int sub = g / GI, gi = g % GI;
   const int MD = pr.M * D;
-  const int LP2 = pr.L * 2 * P, LP1 = pr.L * P;
 
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
   const VT *__restrict__ grad_out = static_cast<const VT *>(pr.grad_out);
-  const float *__restrict__ loc = static_cast<const float *>(pr.loc);
-  const float *__restrict__ attn = static_cast<const float *>(pr.attn);
   float *__restrict__ gacc = static_cast<float *>(pr.grad_value_acc);
-  float *__restrict__ grad_loc = static_cast<float *>(pr.grad_loc);
-  float *__restrict__ grad_attn = static_cast<float *>(pr.grad_attn);
 
   for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
     const UnitCtx uc = decode_unit(pr, tb, unit);
@@ -93,22 +89,8 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         const int H = tb.H[lc], W = tb.W[lc];
 
         float xy[2 * P], a[P];
-        {
-          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + item * LP2 + lc * (2 * P));
-          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + item * LP1 + lc * P);
-#pragma unroll
-          for (int v = 0; v < P / 2; ++v) {
-            const uint4 u = gather16(lp + v, act);
-            xy[4 * v + 0] = __uint_as_float(u.x); xy[4 * v + 1] = __uint_as_float(u.y);
-            xy[4 * v + 2] = __uint_as_float(u.z); xy[4 * v + 3] = __uint_as_float(u.w);
-          }
-#pragma unroll
-          for (int v = 0; v < P / 4; ++v) {
-            const uint4 u = gather16(ap + v, act);
-            a[4 * v + 0] = __uint_as_float(u.x); a[4 * v + 1] = __uint_as_float(u.y);
-            a[4 * v + 2] = __uint_as_float(u.z); a[4 * v + 3] = __uint_as_float(u.w);
-          }
-        }
+        OffsetScale sc;
+        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, xy, a, sc);
         const long long row_off = (long long)(it.b * pr.S + tb.start[lc]) * MD + it.m * D;
         const VT *slab = value + row_off + j * CH;
         // fp32 accumulator row of this head.  fp32 value: natural channel order (it IS grad_value).
@@ -183,30 +165,30 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         reduce_scatter<NV, LPG / 2>(d, j);
 
         // Which point(s) this lane now owns, and with which of the four dot products.
-        float *gl = grad_loc + item * LP2 + lc * (2 * P);
-        float *ga = grad_attn + item * LP1 + lc * P;
+        constexpr int NOWN = C >= 4 ? C / 4 : 1;      // points owned by this lane
+        constexpr int LPP = C >= 4 ? 1 : 4 / C;       // lanes sharing one point
+        const int part = j % LPP;
+        float o_gx[NOWN], o_gy[NOWN], o_gw[NOWN], o_a[NOWN];
+        int o_p[NOWN];
         if constexpr (C >= 4) {
 #pragma unroll
-          for (int t = 0; t < C / 4; ++t) {
-            const int p = j * (C / 4) + t;
-            float lh = 0.f, lw = 0.f, aw = 0.f;
+          for (int t = 0; t < NOWN; ++t) {
+            const int p = j * NOWN + t;
+            float lh = 0.f, lw = 0.f, aw = 0.f, araw = 0.f;
 #pragma unroll
             for (int pp = 0; pp < P; ++pp)
-              if (pp == p) { lh = g_lh[pp]; lw = g_lw[pp]; aw = g_aw[pp]; }
+              if (pp == p) { lh = g_lh[pp]; lw = g_lw[pp]; aw = g_aw[pp]; araw = a[pp]; }
             const float hh = 1.f - lh, hw = 1.f - lw;
             const float d1 = d[4 * t], d2 = d[4 * t + 1], d3 = d[4 * t + 2], d4 = d[4 * t + 3];
-            const float gx = (float)W * aw * (hh * (d2 - d1) + lh * (d4 - d3));
-            const float gy = (float)H * aw * (hw * (d3 - d1) + lw * (d4 - d2));
-            const float gw = hh * hw * d1 + hh * lw * d2 + lh * hw * d3 + lh * lw * d4;
-            if (act) {
-              *reinterpret_cast<float2 *>(gl + 2 * p) = make_float2(gx, gy);
-              ga[p] = gw;
-            }
+            o_gx[t] = (float)W * aw * (hh * (d2 - d1) + lh * (d4 - d3));
+            o_gy[t] = (float)H * aw * (hw * (d3 - d1) + lw * (d4 - d2));
+            o_gw[t] = hh * hw * d1 + hh * lw * d2 + lh * hw * d3 + lh * lw * d4;
+            o_a[t] = araw;
+            o_p[t] = p;
           }
         } else {
           // C == 2: lanes (2p, 2p+1) hold (d1,d2) / (d3,d4);  C == 1: lanes 4p..4p+3 hold d1..d4.
-          constexpr int LPP = 4 / C;               // lanes per point
-          const int p = j / LPP, part = j % LPP;
+          const int p = j / LPP;
           float d1, d2, d3, d4;
           if constexpr (C == 2) {
             const float o0 = __shfl_xor_sync(0xffffffffu, d[0], 1);
@@ -221,18 +203,62 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             d1 = (part & 2) ? plo : lo; d2 = (part & 2) ? phi : hi;
             d3 = (part & 2) ? lo : plo; d4 = (part & 2) ? hi : phi;
           }
-          float lh = 0.f, lw = 0.f, aw = 0.f;
+          float lh = 0.f, lw = 0.f, aw = 0.f, araw = 0.f;
 #pragma unroll
           for (int pp = 0; pp < P; ++pp)
-            if (pp == p) { lh = g_lh[pp]; lw = g_lw[pp]; aw = g_aw[pp]; }
+            if (pp == p) { lh = g_lh[pp]; lw = g_lw[pp]; aw = g_aw[pp]; araw = a[pp]; }
           const float hh = 1.f - lh, hw = 1.f - lw;
-          const float gx = (float)W * aw * (hh * (d2 - d1) + lh * (d4 - d3));
-          const float gy = (float)H * aw * (hw * (d3 - d1) + lw * (d4 - d2));
-          const float gw = hh * hw * d1 + hh * lw * d2 + lh * hw * d3 + lh * lw * d4;
-          if (act && p < P) {
-            if (part == 0) gl[2 * p] = gx;
-            if (part == 1) gl[2 * p + 1] = gy;
-            if (part == LPP - 1) ga[p] = gw;
+          o_gx[0] = (float)W * aw * (hh * (d2 - d1) + lh * (d4 - d3));
+          o_gy[0] = (float)H * aw * (hw * (d3 - d1) + lw * (d4 - d2));
+          o_gw[0] = hh * hw * d1 + hh * lw * d2 + lh * hw * d3 + lh * lw * d4;
+          o_a[0] = araw;
+          o_p[0] = p;
+        }
+
+        const long long lvl = item * pr.L + lc;
+        if constexpr (PRE == 0) {
+          float *gl = static_cast<float *>(pr.grad_loc) + lvl * (2 * P);
+          float *ga = static_cast<float *>(pr.grad_attn) + lvl * P;
+          if (act) {
+#pragma unroll
+            for (int t = 0; t < NOWN; ++t) {
+              if constexpr (C >= 4) {
+                *reinterpret_cast<float2 *>(gl + 2 * o_p[t]) = make_float2(o_gx[t], o_gy[t]);
+                ga[o_p[t]] = o_gw[t];
+              } else {
+                if (part == 0) gl[2 * o_p[t]] = o_gx[t];
+                if (part == 1) gl[2 * o_p[t] + 1] = o_gy[t];
+                if (part == LPP - 1) ga[o_p[t]] = o_gw[t];
+              }
+            }
+          }
+        } else {
+          // softmax backward needs S = sum over the item's L*P samples of a * d(loss)/da; each point is
+          // counted by one lane, then summed over the item's lanes
+          float part_s = 0.f;
+#pragma unroll
+          for (int t = 0; t < NOWN; ++t)
+            if (act && part == 0) part_s += o_a[t] * o_gw[t];
+          for (int dd = 1; dd < LPG * GI; dd <<= 1) part_s += __shfl_xor_sync(0xffffffffu, part_s, dd);
+          if (act) {
+#pragma unroll
+            for (int t = 0; t < NOWN; ++t) {
+              const float gox = __fdiv_rn(o_gx[t] * sc.mulx, sc.divx), goy = __fdiv_rn(o_gy[t] * sc.muly, sc.divy);
+              const float glg = o_a[t] * (o_gw[t] - part_s);
+              if constexpr (PRE == 1) {
+                float *go_ = static_cast<float *>(pr.grad_loc) + lvl * (2 * P);
+                float *gg_ = static_cast<float *>(pr.grad_attn) + lvl * P;
+                if (part == 0) go_[2 * o_p[t]] = gox;
+                if (part == (LPP > 1 ? 1 : 0)) go_[2 * o_p[t] + 1] = goy;
+                if (part == LPP - 1) gg_[o_p[t]] = glg;
+              } else {
+                __nv_bfloat16 *go_ = static_cast<__nv_bfloat16 *>(pr.grad_loc) + lvl * (2 * P);
+                __nv_bfloat16 *gg_ = static_cast<__nv_bfloat16 *>(pr.grad_attn) + lvl * P;
+                if (part == 0) go_[2 * o_p[t]] = __float2bfloat16_rn(gox);
+                if (part == (LPP > 1 ? 1 : 0)) go_[2 * o_p[t] + 1] = __float2bfloat16_rn(goy);
+                if (part == LPP - 1) gg_[o_p[t]] = __float2bfloat16_rn(glg);
+              }
+            }
           }
         }
       }
@@ -242,11 +268,13 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
 template <typename VT, int D, int P>
 static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
-  if (D == 32 && P == 4 && minb >= 100) {   // profiling ablations (variant bits 6..7), D=32/P=4 only
-    if (minb == 101) bwd_vec_kernel<VT, 32, 4, 2, 1><<<grid, kThreads, 0, stream>>>(pr);
-    else bwd_vec_kernel<VT, 32, 4, 2, 2><<<grid, kThreads, 0, stream>>>(pr);
-    return (int)cudaGetLastError();
+  if constexpr (D == 32 && P == 4) {
+    if (minb == 201) { bwd_vec_kernel<VT, D, P, 2, 0, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 202) { bwd_vec_kernel<VT, D, P, 2, 0, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }   // ablations
+    if (minb == 102) { bwd_vec_kernel<VT, D, P, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
   }
+  if (minb >= 100) return MSDA_E_UNSUPPORTED;
   if (minb == 4) bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
   else if (minb == 3) bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
   else bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);

@@ -40,6 +40,9 @@ struct Problem {
   int tiled;               // 1: enumerate queries as 2-D tiles of their own pyramid level
   int tile_w_log2;         // tile is (kUnitItems >> tile_w_log2) rows x (1 << tile_w_log2) columns
   int acc_permuted;        // backward, bf16 value: accumulator rows use acc_pos() order
+  // fused pre-op (msda_pre.cuh): loc/attn then hold raw offsets/logits, grad_loc/grad_attn their gradients
+  const float *ref;        // reference points (N, Lq, L, ref_dim) fp32
+  int ref_dim;             // 2 or 4
 };
 
 // Position of channel c inside a head's fp32 accumulator row when the row is permuted (bf16 value,

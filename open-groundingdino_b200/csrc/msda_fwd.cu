@@ -17,11 +17,12 @@
 // from the int64 shape table (no host read of device memory).
 #include "msda_common.cuh"
 #include "msda_launch.h"
+#include "msda_pre.cuh"
 
 namespace msda {
 
 // PB = points whose 4 gathers are in flight together (register staging: PB*16 registers)
-template <typename VT, int D, int P, int MINB, int PB>
+template <typename VT, int D, int P, int MINB, int PB, int PRE = 0>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr) {
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
   constexpr int NP = Chan<VT>::kPairs;     // fp32x2 accumulators per lane
@@ -39,11 +40,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
   const int rounds = (pr.L + GI - 1) / GI;
   const int sub = g / GI, gi = g % GI;
   const int MD = pr.M * D;
-  const int LP2 = pr.L * 2 * P, LP1 = pr.L * P;
 
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
-  const float *__restrict__ loc = static_cast<const float *>(pr.loc);
-  const float *__restrict__ attn = static_cast<const float *>(pr.attn);
   VT *__restrict__ out = static_cast<VT *>(pr.out);
 
   for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
@@ -61,24 +59,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         const int lc = act ? l : 0;
         const int H = tb.H[lc], W = tb.W[lc];
 
-        // (x,y) pairs and weights of this level: P*8 + P*4 contiguous bytes, 16-byte aligned
+        // (x,y) pairs and weights of this level (given, or derived from raw offsets/logits: msda_pre.cuh)
         float xy[2 * P], a[P];
-        {
-          const uint4 *lp = reinterpret_cast<const uint4 *>(loc + (long long)it.item * LP2 + lc * (2 * P));
-          const uint4 *ap = reinterpret_cast<const uint4 *>(attn + (long long)it.item * LP1 + lc * P);
-#pragma unroll
-          for (int v = 0; v < P / 2; ++v) {
-            const uint4 u = gather16(lp + v, act);
-            xy[4 * v + 0] = __uint_as_float(u.x); xy[4 * v + 1] = __uint_as_float(u.y);
-            xy[4 * v + 2] = __uint_as_float(u.z); xy[4 * v + 3] = __uint_as_float(u.w);
-          }
-#pragma unroll
-          for (int v = 0; v < P / 4; ++v) {
-            const uint4 u = gather16(ap + v, act);
-            a[4 * v + 0] = __uint_as_float(u.x); a[4 * v + 1] = __uint_as_float(u.y);
-            a[4 * v + 2] = __uint_as_float(u.z); a[4 * v + 3] = __uint_as_float(u.w);
-          }
-        }
+        OffsetScale sc;
+        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, xy, a, sc);
         const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
         const int WMD = W * MD;
 
@@ -134,6 +118,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
 
 template <typename VT, int D, int P>
 static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
+  if constexpr (D == 32 && P == 4) {
+    if (minb == 201) { fwd_vec_kernel<VT, D, P, 3, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 202) { fwd_vec_kernel<VT, D, P, 3, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+  }
+  if (minb > 200) return MSDA_E_UNSUPPORTED;
   if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
   else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, 2><<<grid, kThreads, 0, stream>>>(pr);
   else fwd_vec_kernel<VT, D, P, 2, 4><<<grid, kThreads, 0, stream>>>(pr);

@@ -19,7 +19,8 @@ VARIANT_NO_ZERO, VARIANT_NO_NARROW = 0x100, 0x200
 # every symbol include/msda_b200.h declares (tests/test_cabi_symbols.py checks the two lists agree)
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
-    "msda_backward_finish_bf16", "msda_sample_index", "msda_host_create", "msda_host_destroy", "msda_host_h2d_bytes", "msda_host_d2h_bytes",
+    "msda_backward_finish_bf16", "msda_fused_supported", "msda_fused_forward", "msda_fused_backward",
+    "msda_sample_index", "msda_host_create", "msda_host_destroy", "msda_host_h2d_bytes", "msda_host_d2h_bytes",
     "msda_host_fwd_bwd", "msda_host_submit", "msda_host_wait",
 )
 
@@ -43,6 +44,12 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_backward.argtypes = [vp] * 9 + [i] * 7 + [i, i, i, vp, sz, vp]
     lib.msda_backward_finish_bf16.restype = i
     lib.msda_backward_finish_bf16.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.msda_fused_supported.restype = i
+    lib.msda_fused_supported.argtypes = [i] * 5
+    lib.msda_fused_forward.restype = i
+    lib.msda_fused_forward.argtypes = [vp] * 7 + [i] * 7 + [i, i, i, i, vp]
+    lib.msda_fused_backward.restype = i
+    lib.msda_fused_backward.argtypes = [vp] * 10 + [i] * 7 + [i, i, i, i, vp, sz, vp]
     lib.msda_sample_index.restype = i
     lib.msda_sample_index.argtypes = [vp] * 3 + [i] * 6 + [vp, vp]
     lib.msda_host_create.restype = i

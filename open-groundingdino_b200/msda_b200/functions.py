@@ -148,3 +148,63 @@ class MSDeformAttnFunction(Function):
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
             grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+# ---- fused pre-op ----------------------------------------------------------
+def fused_supported(value, sampling_offsets, attn_logits, reference_points, n_levels, n_points) -> bool:
+    """True when libmsda_b200 can take the raw offsets / logits directly (see include/msda_b200.h)."""
+    if not (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)):
+        return False
+    if sampling_offsets.dtype != attn_logits.dtype or sampling_offsets.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    if reference_points.requires_grad or reference_points.shape[-1] not in (2, 4):
+        return False
+    return bool(_lib.lib().msda_fused_supported(value.shape[-1], n_levels, n_points, _DTYPE_CODE[value.dtype],
+                                                _DTYPE_CODE[sampling_offsets.dtype]))
+
+
+class MSDeformAttnFusedFunction(Function):
+    """softmax + sampling-location arithmetic + multi-scale deformable attention in one kernel each way.
+    forward(value (N,S,M,D), spatial_shapes, level_start_index, sampling_offsets (N,Lq,M,L,P,2),
+            attention_logits (N,Lq,M,L*P), reference_points (N,Lq,L,2|4)) -> (N, Lq, M*D)"""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
+        reference_points = reference_points.detach().to(torch.float32).contiguous()
+        _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                       ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits)))
+        N, S, M, D = value.shape
+        _, Lq, _, L, P, _ = sampling_offsets.shape
+        with torch.cuda.device(value.device):
+            output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+            rc = _lib.lib().msda_fused_forward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+                attention_logits.data_ptr(), reference_points.data_ptr(), output.data_ptr(), N, S, M, D, L, Lq, P,
+                reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], 0,
+                torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "msda_fused_forward")
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points = ctx.saved_tensors
+        grad_output = grad_output.contiguous().to(value.dtype)
+        N, S, M, D = value.shape
+        _, Lq, _, L, P, _ = sampling_offsets.shape
+        code = _DTYPE_CODE[value.dtype]
+        with torch.cuda.device(value.device):
+            grad_value = torch.empty_like(value)
+            grad_offsets = torch.empty_like(sampling_offsets)
+            grad_logits = torch.empty_like(attention_logits)
+            ws_bytes = _lib.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, _lib.MSDA_BWD_ATOMIC)
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
+            rc = _lib.lib().msda_fused_backward(
+                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+                attention_logits.data_ptr(), reference_points.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+                grad_offsets.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, reference_points.shape[-1], code,
+                _DTYPE_CODE[sampling_offsets.dtype], 0, workspace.data_ptr() if workspace is not None else None, ws_bytes,
+                torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "msda_fused_backward")
+        return grad_value, None, None, grad_offsets, grad_logits, None
