@@ -207,8 +207,8 @@ class OurLayer:
         if ev1 is not None:
             ev1.record()
         if self.code == L.MSDA_BF16:
-            N, S, M_, D_ = i["dims"][:4]
-            L.check(self.lib.msda_backward_finish_bf16(self.ws.data_ptr(), self.gv.data_ptr(), N, S, M_, D_, stream), "finish")
+            N, S, M_, D_, L_ = i["dims"][:5]
+            L.check(self.lib.msda_backward_finish_bf16(self.ws.data_ptr(), self.gv.data_ptr(), N, S, M_, D_, L_, stream), "finish")
 
 
 def cpu_reference_step(torch, cfg, threads, seed=1234):

@@ -97,7 +97,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 /* Last stage of a bf16 backward that was launched with MSDA_VARIANT_NO_NARROW: rounds the fp32
  * accumulator held in `workspace` (library-private row layout) to bf16 grad_value (N, S, M, D). */
 int msda_backward_finish_bf16(const void *workspace, void *grad_value, int batch, int spatial_size,
-                              int num_heads, int channels, void *stream);
+                              int num_heads, int channels, int num_levels, void *stream);
 
 /* ---- fused pre-op (next row f1 of the scope table) --------------------------------------------------
  * MSDeformAttn.forward computes attention_weights = softmax(logits over L*P) and sampling_locations =

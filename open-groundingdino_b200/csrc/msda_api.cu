@@ -48,7 +48,9 @@ int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool
 
 // The bf16 backward accumulates fp32 rows in the permuted channel order of acc_pos() whenever the head
 // width allows it; a function of (dtype, D) only, so every kernel family and the narrowing agree.
-bool acc_is_permuted(int dtype, int D) { return dtype == MSDA_BF16 && D % 8 == 0; }
+// Exception: D = 32 with at least two levels uses the pair-cooperative whole-row reductions of msda_bwd.cu,
+// which write the natural channel order.
+bool acc_is_permuted(int dtype, int D, int L) { return dtype == MSDA_BF16 && D % 8 == 0 && !(D == 32 && L >= 2); }
 
 // variant bits 4..5: CTAs per SM the vector kernels are compiled for (1 -> 2, 2 -> 3, 3 -> 4); 0 picks the
 // measured best: 3 for the forward (gather-latency bound, profits from 24 resident warps), 2 for the
@@ -140,7 +142,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 
   // atomic mode: accumulate into fp32 (fp64) -- grad_value itself, or the workspace for bf16
   void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
-  pr.acc_permuted = acc_is_permuted(dtype, D);
+  pr.acc_permuted = acc_is_permuted(dtype, D, L);
   const size_t acc_bytes = n_value * (dtype == MSDA_F64 ? 8 : 4);
   if (!(variant & MSDA_VARIANT_NO_ZERO))
     if (cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, stream)) return (int)e;
@@ -215,7 +217,7 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
   void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
-  pr.acc_permuted = acc_is_permuted(dtype, D);
+  pr.acc_permuted = acc_is_permuted(dtype, D, L);
   pr.grad_value_acc = acc;
   if (!(aligned16(value) && aligned16(sampling_offsets) && aligned16(attn_logits) && aligned16(reference_points) &&
         aligned16(grad_output) && aligned16(acc)))
@@ -229,10 +231,10 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
   return rc;
 }
 
-int msda_backward_finish_bf16(const void *workspace, void *grad_value, int N, int S, int M, int D, void *stream_) {
-  if (!workspace || !grad_value || N <= 0 || S <= 0 || M <= 0 || D <= 0) return MSDA_E_INVALID;
+int msda_backward_finish_bf16(const void *workspace, void *grad_value, int N, int S, int M, int D, int L, void *stream_) {
+  if (!workspace || !grad_value || N <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0) return MSDA_E_INVALID;
   return launch_f32_to_bf16(static_cast<const float *>(workspace), grad_value, (long long)N * S * M * D, D,
-                            acc_is_permuted(MSDA_BF16, D), static_cast<cudaStream_t>(stream_));
+                            acc_is_permuted(MSDA_BF16, D, L), static_cast<cudaStream_t>(stream_));
 }
 
 int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index, const float *sampling_loc,

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   constexpr int G = 32 / LPG;
   constexpr int NV = 4 * P;                       // dot products per (item, level)
   constexpr int C = NV >= LPG ? NV / LPG : 1;     // of which a lane owns C after the reduce-scatter
+  constexpr bool COOP = (CH == 8 && LPG == 4);    // pairs of level groups send whole accumulator rows
 
   __shared__ Tables tb;
   load_tables(pr, tb);
@@ -106,6 +107,18 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         // in registers and sent as one set of reductions (warp-level aggregation before the L2 atomics)
         float pend[4] = {0.f, 0.f, 0.f, 0.f};
         int pend_off = 0, pend_mask = 0;
+        // COOP (bf16, 4 lanes per row): two level groups of the same item pair up so that every reduction
+        // instruction covers WHOLE 128-byte accumulator rows -- lanes of the first group send channels
+        // [8j, 8j+4), lanes of the second [8j+4, 8j+8), first of the first group's row, then of the second's.
+        // Both groups hold the same grad_output (same item, same head), so only the row offset and the
+        // coefficient travel (two xor-shuffles per neighbour).  The L2 atomic units take whole rows ~20 %
+        // faster than the same bytes as two half rows (profiles/r01_microbench_scatter.txt).
+        const bool coop = COOP && !pr.acc_permuted;
+        const bool first = (lane & LPG) == 0;
+        const unsigned long long gsel0 = (COOP && !first) ? go[NP / 2] : go[0];
+        const unsigned long long gsel1 = (COOP && !first) ? go[NP / 2 + 1] : go[1];
+        float *gcoop = gacc + (long long)(it.b * pr.S) * MD + it.m * D + j * CH + (first ? 0 : 4);
+        const int lvl_off = tb.start[lc] * MD;
         auto flush = [&]() {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -147,9 +160,33 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             unpack_f2(dot2, dlo, dhi);
             d[4 * p + kk] = dlo + dhi;
           }
-          // same cell <=> same offset AND same neighbour mask: (h, W-1) and (h+1, -1) share the
-          // row-major offset but never the mask
-          if (p > 0 && in && mask == pend_mask && o00 == pend_off) {
+          if (coop) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const float my_c = ((mask >> kk) & 1) ? cw[kk] : 0.f;
+              const int my_off = lvl_off + o00 + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
+              const float o_c = __shfl_xor_sync(0xffffffffu, my_c, LPG);
+              const int o_off = __shfl_xor_sync(0xffffffffu, my_off, LPG);
+              const float c_a = first ? my_c : o_c, c_b = first ? o_c : my_c;
+              const int off_a = first ? my_off : o_off, off_b = first ? o_off : my_off;
+              if (ABL != 1 && c_a != 0.f) {
+                float r0, r1, r2, r3;
+                const unsigned long long c2 = pack_f2(c_a, c_a);
+                unpack_f2(fmul2(c2, gsel0), r0, r1);
+                unpack_f2(fmul2(c2, gsel1), r2, r3);
+                red_add_f32x4(gcoop + off_a, r0, r1, r2, r3);
+              }
+              if (ABL != 1 && c_b != 0.f) {
+                float r0, r1, r2, r3;
+                const unsigned long long c2 = pack_f2(c_b, c_b);
+                unpack_f2(fmul2(c2, gsel0), r0, r1);
+                unpack_f2(fmul2(c2, gsel1), r2, r3);
+                red_add_f32x4(gcoop + off_b, r0, r1, r2, r3);
+              }
+            }
+          } else if (p > 0 && in && mask == pend_mask && o00 == pend_off) {
+            // same cell <=> same offset AND same neighbour mask: (h, W-1) and (h+1, -1) share the
+            // row-major offset but never the mask
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) pend[kk] += cw[kk];
           } else {
@@ -160,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             pend_mask = mask;
           }
         }
-        flush();
+        if (!coop) flush();
 
         reduce_scatter<NV, LPG / 2>(d, j);
 

@@ -43,7 +43,7 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_backward.restype = i
     lib.msda_backward.argtypes = [vp] * 9 + [i] * 7 + [i, i, i, vp, sz, vp]
     lib.msda_backward_finish_bf16.restype = i
-    lib.msda_backward_finish_bf16.argtypes = [vp, vp, i, i, i, i, vp]
+    lib.msda_backward_finish_bf16.argtypes = [vp, vp, i, i, i, i, i, vp]
     lib.msda_fused_supported.restype = i
     lib.msda_fused_supported.argtypes = [i] * 5
     lib.msda_fused_forward.restype = i
