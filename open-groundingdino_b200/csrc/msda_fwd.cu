@@ -82,10 +82,18 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
             const float ah = hh * aw, al = lh * aw;
             wt[pp][0] = ah * hw; wt[pp][1] = ah * lw; wt[pp][2] = al * hw; wt[pp][3] = al * lw;
             const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
-            raw[pp][0] = gather16(p00, mask & 1);
-            raw[pp][1] = gather16(p00 + MD, mask & 2);
-            raw[pp][2] = gather16(p00 + WMD, mask & 4);
-            raw[pp][3] = gather16(p00 + WMD + MD, mask & 8);
+            // fp32 only: measured +6-14 % there, -5-10 % for bf16 (the branch costs more than the zero fill)
+            if (CH == 4 && mask == 15) {   // interior cell (the common case): four plain loads, no predicates
+              raw[pp][0] = __ldg(reinterpret_cast<const uint4 *>(p00));
+              raw[pp][1] = __ldg(reinterpret_cast<const uint4 *>(p00 + MD));
+              raw[pp][2] = __ldg(reinterpret_cast<const uint4 *>(p00 + WMD));
+              raw[pp][3] = __ldg(reinterpret_cast<const uint4 *>(p00 + WMD + MD));
+            } else {
+              raw[pp][0] = gather16(p00, mask & 1);
+              raw[pp][1] = gather16(p00 + MD, mask & 2);
+              raw[pp][2] = gather16(p00 + WMD, mask & 4);
+              raw[pp][3] = gather16(p00 + WMD + MD, mask & 8);
+            }
           }
 #pragma unroll
           for (int pp = 0; pp < PB; ++pp) {
