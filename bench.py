@@ -392,6 +392,7 @@ def run_ours(args, cfg):
     extra = {}
     if rank == 0 and not args.no_ref_cuda:
         extra["reference_cuda_op"] = time_reference_cuda(torch, layers, cfg, ms_step)
+        extra["reference_grid_sample_cuda"] = time_grid_sample_cuda(torch, layers, cfg, ms_step)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -484,6 +485,41 @@ def emit(line):
     sys.stdout.flush()
     data = (json.dumps(line) + "\n").encode()
     os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
+def time_grid_sample_cuda(torch, layers, cfg, ours_ms_step):
+    """The grid_sample formulation on the GPU -- what the PAVE fork actually executes
+    (models/GroundingDINO/ms_deform_attn.py:339-341, CUDA call commented out) -- via oracle/torch_port.py, fp32
+    (grid_sample needs value and grid in one dtype), autograd backward, same tensors and step structure."""
+    try:
+        from oracle import torch_port
+        shapes = [tuple(x) for x in cfg["shapes"]]
+        bf16 = cfg["dtype"] == "bf16"
+
+        def step():
+            outs = []
+            for lay in layers:
+                i = lay.i
+                v = i["value"].float().requires_grad_(True)
+                s = i["loc"].clone().requires_grad_(True)
+                a = i["attn"].clone().requires_grad_(True)
+                o = torch_port.msda_grid_sample(v, shapes, s, a)
+                outs.append((o.to(torch.bfloat16) if bf16 else o, v, s, a, i["grad_out"]))
+            for o, v, s, a, g in reversed(outs):
+                o.backward(g.reshape(o.shape))
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        return {"ms_per_step": ms, "speedup_ours": ms / ours_ms_step, "note": "grid_sample path on the same GPU, fp32 + autograd"}
+    except Exception as exc:   # e.g. out of memory on a shared box
+        return {"unavailable": repr(exc)[:160]}
 
 
 def main():

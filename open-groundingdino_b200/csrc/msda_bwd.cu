@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
       const long long item = it.item;
 
       unsigned long long go[NP];
-      Chan<VT>::unpack2(gather16(grad_out + item * D + j * CH, it.valid), go);
+      Chan<VT>::unpack2(Chan<VT>::gather(grad_out + item * D + j * CH, it.valid), go);
 
       for (int r = 0; r < rounds; ++r) {
         const int l = r * GI + gi;
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         // bf16 value: the row is stored as [first halves of every lane's 8 channels | second halves]
         // (acc_pos() in msda_common.cuh) so each 16-byte reduction of a 4-lane group lands in ONE
         // fully-used 64-byte span instead of half of every 32-byte sector.
-        float *gslab = gacc + row_off + j * 4;
+        float *gslab = gacc + row_off + (pr.acc_permuted ? j * 4 : j * CH);
+        const int chunk_stride = pr.acc_permuted ? D / 2 : 4;     // second 4-channel chunk of a lane's 8
         const int WMD = W * MD;
 
         float d[NV];
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         // Both groups hold the same grad_output (same item, same head), so only the row offset and the
         // coefficient travel (two xor-shuffles per neighbour).  The L2 atomic units take whole rows ~20 %
         // faster than the same bytes as two half rows (profiles/r01_microbench_scatter.txt).
-        const bool coop = COOP && !pr.acc_permuted;
+        const bool coop = COOP && !pr.acc_permuted && GI >= 2;   // the partner group must belong to the same item
         const bool first = (lane & LPG) == 0;
         const unsigned long long gsel0 = (COOP && !first) ? go[NP / 2] : go[0];
         const unsigned long long gsel1 = (COOP && !first) ? go[NP / 2 + 1] : go[1];
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
                 float r0, r1, r2, r3;
                 unpack_f2(fmul2(c2, go[2 * h4]), r0, r1);
                 unpack_f2(fmul2(c2, go[2 * h4 + 1]), r2, r3);
-                red_add_f32x4(gslab + off + h4 * (D / 2), r0, r1, r2, r3);
+                red_add_f32x4(gslab + off + h4 * chunk_stride, r0, r1, r2, r3);
               }
             }
           }
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             const bool on = (mask >> kk) & 1;
             const int off = o00 + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
             unsigned long long v[NP];
-            Chan<VT>::unpack2(gather16(slab + off, on && ABL != 2), v);
+            Chan<VT>::unpack2(Chan<VT>::gather(slab + off, on && ABL != 2), v);
             unsigned long long dot2 = 0ull;
 #pragma unroll
             for (int cidx = 0; cidx < NP; ++cidx) dot2 = ffma2(go[cidx], v[cidx], dot2);
@@ -328,6 +329,7 @@ static int dispatch_bwd(const Problem &pr, int grid, int minb, cudaStream_t stre
 }
 
 int launch_backward_vec(const Problem &pr, int dtype, int grid, int minb, cudaStream_t stream) {
+  if (dtype == MSDA_F32 && pr.D >= 32) return dispatch_bwd<wide_f32>(pr, grid, minb, stream);   // 8 channels per lane
   if (dtype == MSDA_F32) return dispatch_bwd<float>(pr, grid, minb, stream);
   if (dtype == MSDA_BF16) return dispatch_bwd<__nv_bfloat16>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;

@@ -234,12 +234,32 @@ __device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsign
   return d;
 }
 
+// Read-only 16-byte gather; a false predicate yields zeros without touching memory.
+__device__ __forceinline__ uint4 gather16(const void *p, bool pred) {
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (pred) v = __ldg(reinterpret_cast<const uint4 *>(p));
+  return v;
+}
+
+// fp32 rows handled 8 channels (32 bytes) per lane: half the lanes per row, so a warp pass covers two items
+// and the per-item geometry / bookkeeping instructions halve (the fp32 kernels are issue-bound).
+struct wide_f32 {
+  float x;
+};
+struct Raw32 {
+  uint4 lo, hi;
+};
+
 // ---- 16-byte channel vectors ---------------------------------------------------------------------
 template <typename VT>
 struct Chan;
 
 template <>
 struct Chan<float> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw gather(const float *p, bool pred) { return gather16(p, pred); }
+  static __device__ __forceinline__ Raw gather_plain(const float *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+  static __device__ __forceinline__ void store(float *p, const Raw &r) { *reinterpret_cast<uint4 *>(p) = r; }
   static constexpr int kPerLane = 4;
   static __device__ __forceinline__ void unpack(const uint4 &u, float (&f)[4]) {
     f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
@@ -256,7 +276,46 @@ struct Chan<float> {
 };
 
 template <>
+struct Chan<wide_f32> {
+  using Raw = Raw32;
+  static constexpr int kPerLane = 8;
+  static constexpr int kPairs = 4;
+  static __device__ __forceinline__ Raw gather(const wide_f32 *p, bool pred) {
+    Raw r;
+    r.lo = gather16(p, pred);
+    r.hi = gather16(p + 4, pred);
+    return r;
+  }
+  static __device__ __forceinline__ Raw gather_plain(const wide_f32 *p) {
+    Raw r;
+    r.lo = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.hi = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+    return r;
+  }
+  static __device__ __forceinline__ void store(wide_f32 *p, const Raw &r) {
+    reinterpret_cast<uint4 *>(p)[0] = r.lo;
+    reinterpret_cast<uint4 *>(p)[1] = r.hi;
+  }
+  static __device__ __forceinline__ void unpack2(const Raw &u, unsigned long long (&q)[4]) {
+    q[0] = pack_f2(__uint_as_float(u.lo.x), __uint_as_float(u.lo.y));
+    q[1] = pack_f2(__uint_as_float(u.lo.z), __uint_as_float(u.lo.w));
+    q[2] = pack_f2(__uint_as_float(u.hi.x), __uint_as_float(u.hi.y));
+    q[3] = pack_f2(__uint_as_float(u.hi.z), __uint_as_float(u.hi.w));
+  }
+  static __device__ __forceinline__ Raw pack(const float (&f)[8]) {
+    Raw r;
+    r.lo = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    r.hi = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
+    return r;
+  }
+};
+
+template <>
 struct Chan<__nv_bfloat16> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw gather(const __nv_bfloat16 *p, bool pred) { return gather16(p, pred); }
+  static __device__ __forceinline__ Raw gather_plain(const __nv_bfloat16 *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+  static __device__ __forceinline__ void store(__nv_bfloat16 *p, const Raw &r) { *reinterpret_cast<uint4 *>(p) = r; }
   static constexpr int kPerLane = 8;
   // bf16 -> fp32 is a 16-bit shift: exact, one ALU op per channel.
   static __device__ __forceinline__ void unpack(const uint4 &u, float (&f)[8]) {
@@ -280,13 +339,6 @@ struct Chan<__nv_bfloat16> {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
   }
 };
-
-// Read-only 16-byte gather; a false predicate yields zeros without touching memory.
-__device__ __forceinline__ uint4 gather16(const void *p, bool pred) {
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (pred) v = __ldg(reinterpret_cast<const uint4 *>(p));
-  return v;
-}
 
 // Vector reduction: one 16-byte fp32x4 add performed by the L2 atomic unit (REDG.E.ADD.F32x4).
 __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d) {

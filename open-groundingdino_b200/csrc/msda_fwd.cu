@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
 
 #pragma unroll
         for (int p0 = 0; p0 < P; p0 += PB) {
-          uint4 raw[PB][4];
+          typename Chan<VT>::Raw raw[PB][4];
           float wt[PB][4];
 #pragma unroll
           for (int pp = 0; pp < PB; ++pp) {
@@ -83,16 +83,16 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
             wt[pp][0] = ah * hw; wt[pp][1] = ah * lw; wt[pp][2] = al * hw; wt[pp][3] = al * lw;
             const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
             // fp32 only: measured +6-14 % there, -5-10 % for bf16 (the branch costs more than the zero fill)
-            if (CH == 4 && mask == 15) {   // interior cell (the common case): four plain loads, no predicates
-              raw[pp][0] = __ldg(reinterpret_cast<const uint4 *>(p00));
-              raw[pp][1] = __ldg(reinterpret_cast<const uint4 *>(p00 + MD));
-              raw[pp][2] = __ldg(reinterpret_cast<const uint4 *>(p00 + WMD));
-              raw[pp][3] = __ldg(reinterpret_cast<const uint4 *>(p00 + WMD + MD));
+            if (sizeof(VT) == 4 && mask == 15) {   // interior cell (the common case): plain loads, no predicates
+              raw[pp][0] = Chan<VT>::gather_plain(p00);
+              raw[pp][1] = Chan<VT>::gather_plain(p00 + MD);
+              raw[pp][2] = Chan<VT>::gather_plain(p00 + WMD);
+              raw[pp][3] = Chan<VT>::gather_plain(p00 + WMD + MD);
             } else {
-              raw[pp][0] = gather16(p00, mask & 1);
-              raw[pp][1] = gather16(p00 + MD, mask & 2);
-              raw[pp][2] = gather16(p00 + WMD, mask & 4);
-              raw[pp][3] = gather16(p00 + WMD + MD, mask & 8);
+              raw[pp][0] = Chan<VT>::gather(p00, mask & 1);
+              raw[pp][1] = Chan<VT>::gather(p00 + MD, mask & 2);
+              raw[pp][2] = Chan<VT>::gather(p00 + WMD, mask & 4);
+              raw[pp][3] = Chan<VT>::gather(p00 + WMD + MD, mask & 8);
             }
           }
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         for (int c = 0; c < CH; ++c) res[c] += __shfl_xor_sync(0xffffffffu, res[c], d);
       }
       if (it.valid && gi == 0) {
-        *reinterpret_cast<uint4 *>(out + (long long)it.item * D + j * CH) = Chan<VT>::pack(res);
+        Chan<VT>::store(out + (long long)it.item * D + j * CH, Chan<VT>::pack(res));
       }
     }
   }
@@ -126,14 +126,17 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
 
 template <typename VT, int D, int P>
 static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
+  // points staged together: PB * 4 gathers * (16 or 32 bytes) of registers per lane
+  constexpr int WR = sizeof(typename Chan<VT>::Raw) / 16;
+  constexpr int PB2 = 4 / WR, PB3 = 2 / WR;
   if constexpr (D == 32 && P == 4) {
-    if (minb == 201) { fwd_vec_kernel<VT, D, P, 3, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 202) { fwd_vec_kernel<VT, D, P, 3, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 201) { fwd_vec_kernel<VT, D, P, 3, PB3, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 202) { fwd_vec_kernel<VT, D, P, 3, PB3, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
   }
   if (minb > 200) return MSDA_E_UNSUPPORTED;
   if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
-  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, 2><<<grid, kThreads, 0, stream>>>(pr);
-  else fwd_vec_kernel<VT, D, P, 2, 4><<<grid, kThreads, 0, stream>>>(pr);
+  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, PB3><<<grid, kThreads, 0, stream>>>(pr);
+  else fwd_vec_kernel<VT, D, P, 2, PB2><<<grid, kThreads, 0, stream>>>(pr);
   return (int)cudaGetLastError();
 }
 
@@ -154,6 +157,7 @@ bool fwd_vec_supported(int dtype, int D, int P, int L) {
 }
 
 int launch_forward_vec(const Problem &pr, int dtype, int grid, int minb, cudaStream_t stream) {
+  if (dtype == MSDA_F32 && pr.D >= 32) return dispatch_fwd<wide_f32>(pr, grid, minb, stream);   // 8 channels per lane
   if (dtype == MSDA_F32) return dispatch_fwd<float>(pr, grid, minb, stream);
   if (dtype == MSDA_BF16) return dispatch_fwd<__nv_bfloat16>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;
