@@ -98,3 +98,20 @@ def test_sampling_locations_forms():
     assert torch.allclose(loc[0, 2, 0, 1, 0], ref4[0, 2, 1, :2] + off[0, 2, 0, 1, 0] / 3 * ref4[0, 2, 1, 2:] * 0.5)
     with pytest.raises(ValueError):
         sampling_locations_from(torch.rand(1, 5, 2, 3), off, sh, 3)
+
+
+def test_reference_arm_prints_one_schema_complete_json_line():
+    """`bench.py --impl reference` is the CPU arm the driver runs; it must print exactly one JSON line with the
+    contract's keys (the GPU arm's line is checked on the box)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, check=True).stdout.strip().splitlines()
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
