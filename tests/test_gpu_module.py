@@ -229,3 +229,32 @@ def test_no_out_of_bounds_writes(dtype):
         for a in (a_out, a_gv, a_gl, a_ga, a_ws):
             assert (a[:PAD] == 7).all() and (a[-PAD:] == 7).all()
     assert torch.isfinite(out.float()).all() and torch.isfinite(gv.float()).all()
+
+
+def test_cuda_graph_capture_and_replay():
+    """The op only enqueues work on the caller's stream (no allocation, sync or host read inside the library), so a
+    forward + backward can be captured in a CUDA graph and replayed on new data."""
+    from msda_b200 import ms_deform_attn_backward, ms_deform_attn_forward
+    g = make_inputs(SHAPES, N=2, M=8, D=32, Lq=None, P=4, dist="W", seed=41)
+    t = lambda k, dt=None: torch.from_numpy(g[k]).cuda() if dt is None else torch.from_numpy(g[k]).cuda().to(dt)
+    for dt in (torch.float32, torch.bfloat16):
+        value, gout = t("value", dt), t("grad_out", dt)
+        sh, st, loc, attn = t("shapes"), t("starts"), t("loc"), t("attn")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):      # warm-up outside capture
+            ms_deform_attn_backward(value, sh, st, loc, attn, gout, 64)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = ms_deform_attn_forward(value, sh, st, loc, attn, 64)
+            gv, gl, ga = ms_deform_attn_backward(value, sh, st, loc, attn, gout, 64)
+        new_value = torch.randn_like(value.float()).to(dt)
+        value.copy_(new_value)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = ms_deform_attn_forward(new_value, sh, st, loc, attn, 64)
+        wgv, wgl, wga = ms_deform_attn_backward(new_value, sh, st, loc, attn, gout, 64)
+        assert torch.equal(out, want) and torch.equal(gl, wgl) and torch.equal(ga, wga)
+        tol = 1e-5 if dt == torch.float32 else 1e-2
+        assert oracle.normwise(gv.float().cpu().numpy(), wgv.float().cpu().numpy()) < tol
