@@ -47,6 +47,14 @@ CONFIGS = {
                  text="SwinT-OGC 800x1333 encoder MSDeformAttn fwd+bwd, bs=1, fp32 (6 independent layers per step)"),
     "cfg3": dict(shapes=SWIN_T_800x1333, N=8, Lq=900, dtype="f32", layers=6,
                  text="SwinT-OGC decoder cross-attention MSDeformAttn fwd+bwd, 900 queries, bs=8, fp32, 6 layers"),
+    "cfg3bf16": dict(shapes=SWIN_T_800x1333, N=8, Lq=900, dtype="bf16", layers=6,
+                     text="SwinT-OGC decoder cross-attention MSDeformAttn fwd+bwd, 900 queries, bs=8, bf16 value, 6 layers"),
+    "cfg4enc": dict(shapes=[(128, 128), (64, 64), (32, 32), (16, 16)], N=4, Lq=None, dtype="bf16", layers=6,
+                    text="SwinB 1024x1024 encoder MSDeformAttn fwd+bwd, bs=4/GPU, bf16 value (op part of BASELINE configs[3])"),
+    "cfg4dec": dict(shapes=[(128, 128), (64, 64), (32, 32), (16, 16)], N=4, Lq=900, dtype="bf16", layers=6,
+                    text="SwinB 1024x1024 decoder cross-attention MSDeformAttn fwd+bwd, 900 queries, bs=4/GPU, bf16 value"),
+    "pave512": dict(shapes=[(64, 64), (32, 32), (16, 16), (8, 8)], N=4, Lq=None, dtype="bf16", layers=6,
+                    text="PAVE 512x512 training-crop encoder MSDeformAttn fwd+bwd (config/cfg_odvg.py:2-4), bs=4, bf16 value"),
 }
 M, D, P = 8, 32, 4
 

@@ -201,3 +201,23 @@ def test_deterministic_mode_full_size():
     assert np.array_equal(a[1], b[1])
     atomic = run_cuda(g, torch.float32, mode=0)
     assert oracle.normwise(a[1], atomic[1]) < 1e-5     # the atomic mode's own fp32 summation noise
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_reference_gradcheck_fp64(channels):
+    """The reference's own gradient test (OPS/test.py:63-78,85-86): torch.autograd.gradcheck of the autograd Function
+    in fp64 on its fixture (N,M = 1,2; Lq,L,P = 2,2,2; shapes (6,4),(3,2); seed 3), for the channel counts it visits."""
+    from torch.autograd import gradcheck
+    from msda_b200 import MSDeformAttnFunction
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    level_start_index = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    value = torch.rand(N, S, M, channels).cuda() * 0.01
+    sampling_locations = torch.rand(N, Lq, M, L, P, 2).cuda()
+    attention_weights = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    attention_weights /= attention_weights.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    args = (value.double().requires_grad_(True), shapes, level_start_index,
+            sampling_locations.double().requires_grad_(True), attention_weights.double().requires_grad_(True), 2)
+    assert gradcheck(MSDeformAttnFunction.apply, args)
