@@ -2,11 +2,14 @@
 // ms_deformable_col2im_gpu_kernel_* variants, reference ms_deform_im2col_cuda.cuh:301-920, the
 // per-sample routine :87-159 and the launcher :956-1327).
 //
-// Same item/level/lane mapping as the forward (msda_fwd.cu).  Per sample a lane holds 16 bytes of
+// Same item/level/lane mapping as the forward (msda_fwd.cu).  Per sample a lane holds 16 or 32 bytes of
 // each of the 4 neighbour rows and of grad_output, and produces
-//   * the grad_value contribution  w_k * attn * grad_out  as ONE 16-byte vector reduction per
-//     neighbour (REDG.E.ADD.F32x4, executed by the L2 atomic units) instead of the reference's
-//     scalar atomicAdd per channel -- 4x fewer atomic requests, each a full 128-byte row per 8 lanes;
+//   * the grad_value contribution  w_k * attn * grad_out  as 16-byte vector reductions
+//     (REDG.E.ADD.F32x4, executed by the L2 atomic units) instead of the reference's scalar atomicAdd per
+//     channel.  With 8 lanes per row (narrow fp32) one instruction covers 4 whole 128-byte rows; with 4 lanes
+//     per row (bf16, wide fp32) two level groups of the same item pair up (COOP below) so that every
+//     instruction still covers whole rows -- the L2 atomic units are the bound of this kernel and take
+//     whole rows ~20 % faster than the same bytes as half rows.  Zero coefficients send nothing;
 //   * four partial dot products d_k = <grad_out, v_k> over its channels.  Everything the two small
 //     gradients need is linear in the d_k:
 //         grad_attn  = w1 d1 + w2 d2 + w3 d3 + w4 d4
