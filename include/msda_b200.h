@@ -23,7 +23,8 @@
  *       value             (N, S, M, D)          dtype = value_dtype
  *       spatial_shapes    (L, 2) int64, (H, W)  device memory, read by the kernels (no host sync)
  *       level_start_index (L)    int64          device memory
- *       sampling_loc      (N, Lq, M, L, P, 2)   (x, y) normalised to [0,1]; fp32 (fp64 for MSDA_F64)
+ *       sampling_loc      (N, Lq, M, L, P, 2)   (x, y) normalised to [0,1]; fp32 (fp64 for MSDA_F64), also for
+ *                                               16-bit values: a 16-bit pixel coordinate is useless
  *       attn_weight       (N, Lq, M, L, P)      fp32 (fp64 for MSDA_F64)
  *       output            (N, Lq, M*D)          dtype = value_dtype
  *       grad_output/grad_value like output/value; grad_sampling_loc/grad_attn_weight like their inputs
@@ -46,7 +47,7 @@ extern "C" {
 #define MSDA_ABI_VERSION 1
 
 /* dtype of value / output / grad_output / grad_value */
-enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2 };
+enum { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F64 = 2, MSDA_F16 = 3 };
 
 /* backward accumulation mode for grad_value */
 enum {
@@ -105,7 +106,7 @@ int msda_backward_finish_bf16(const void *workspace, void *grad_value, int batch
  * PyTorch kernels before calling the op (ops/modules/ms_deform_attn.py:98-108).  These entry points take the
  * raw linear-layer outputs instead and do that arithmetic in the kernel prologue (and its transpose in the
  * backward epilogue), so neither tensor round-trips through HBM:
- *   sampling_offsets  (N, Lq, M, L, P, 2)  q_dtype (MSDA_F32 or MSDA_BF16)
+ *   sampling_offsets  (N, Lq, M, L, P, 2)  q_dtype (MSDA_F32, MSDA_BF16 or MSDA_F16)
  *   attn_logits       (N, Lq, M, L*P)      q_dtype
  *   reference_points  (N, Lq, L, ref_dim)  fp32, ref_dim = 2 or 4 (no gradient is produced for them)
  * grad_offsets / grad_logits have the shapes and dtype of their inputs.  Atomic backward mode only.

@@ -22,14 +22,15 @@ int sm_count() {
   return sms;
 }
 
-size_t elem_size(int dtype) { return dtype == MSDA_F64 ? 8 : dtype == MSDA_BF16 ? 2 : 4; }
+bool is16(int dtype) { return dtype == MSDA_BF16 || dtype == MSDA_F16; }
+size_t elem_size(int dtype) { return dtype == MSDA_F64 ? 8 : is16(dtype) ? 2 : 4; }
 size_t coord_size(int dtype) { return dtype == MSDA_F64 ? 8 : 4; }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_dims(int N, int S, int M, int D, int L, int Lq, int P, int dtype) {
   if (N <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq <= 0 || P <= 0) return MSDA_E_INVALID;
-  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F64) return MSDA_E_INVALID;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F64 && dtype != MSDA_F16) return MSDA_E_INVALID;
   // in-slab offsets are 32-bit element indices (like the reference, cuh:47-53)
   if ((long long)S * M * D >= (1LL << 31)) return MSDA_E_TOO_LARGE;
   if ((long long)N * Lq * M >= (1LL << 31) - 64 || (long long)N * S >= (1LL << 31)) return MSDA_E_TOO_LARGE;
@@ -50,7 +51,7 @@ int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool
 // width allows it; a function of (dtype, D) only, so every kernel family and the narrowing agree.
 // Exception: D = 32 with at least two levels uses the pair-cooperative whole-row reductions of msda_bwd.cu,
 // which write the natural channel order.
-bool acc_is_permuted(int dtype, int D, int L) { return dtype == MSDA_BF16 && D % 8 == 0 && !(D == 32 && L >= 2); }
+bool acc_is_permuted(int dtype, int D, int L) { return is16(dtype) && D % 8 == 0 && !(D == 32 && L >= 2); }
 
 // variant bits 4..5: CTAs per SM the vector kernels are compiled for (1 -> 2, 2 -> 3, 3 -> 4); 0 picks the
 // measured best: 3 for the forward (gather-latency bound, profits from 24 resident warps), 2 for the
@@ -110,7 +111,7 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
 size_t msda_backward_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
   if (check_dims(N, S, M, D, L, Lq, P, dtype) != MSDA_OK) return 0;
   if (mode == MSDA_BWD_DETERMINISTIC) return deterministic_workspace_bytes(N, S, M, D, L, Lq, P, dtype);
-  return dtype == MSDA_BF16 ? (size_t)N * S * M * D * sizeof(float) : 0;   // fp32 accumulator for bf16
+  return is16(dtype) ? (size_t)N * S * M * D * sizeof(float) : 0;   // fp32 accumulator for bf16 / fp16
 }
 
 int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -141,7 +142,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
   }
 
   // atomic mode: accumulate into fp32 (fp64) -- grad_value itself, or the workspace for bf16
-  void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
+  void *acc = is16(dtype) ? workspace : grad_value;
   pr.acc_permuted = acc_is_permuted(dtype, D, L);
   const size_t acc_bytes = n_value * (dtype == MSDA_F64 ? 8 : 4);
   if (!(variant & MSDA_VARIANT_NO_ZERO))
@@ -161,8 +162,9 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
   }
   if (rc != MSDA_OK) return rc;
-  if (dtype == MSDA_BF16 && !(variant & MSDA_VARIANT_NO_NARROW))
-    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0, stream);
+  if (is16(dtype) && !(variant & MSDA_VARIANT_NO_NARROW))
+    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0,
+                            dtype == MSDA_F16, stream);
   return rc;
 }
 
@@ -171,6 +173,7 @@ int msda_fused_supported(int D, int L, int P, int value_dtype, int q_dtype) {
   if (D != 32 || P != 4 || L < 1) return 0;
   if (value_dtype == MSDA_F32) return (q_dtype == MSDA_F32 && L <= 4) ? 1 : 0;       // 4 level groups per warp
   if (value_dtype == MSDA_BF16) return ((q_dtype == MSDA_F32 || q_dtype == MSDA_BF16) && L <= 8) ? 1 : 0;
+  if (value_dtype == MSDA_F16) return ((q_dtype == MSDA_F32 || q_dtype == MSDA_F16) && L <= 8) ? 1 : 0;
   return 0;
 }
 
@@ -192,7 +195,7 @@ int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const i
   pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
-  return launch_forward_vec(pr, dtype, vec_grid(pr, 3), q_dtype == MSDA_BF16 ? 202 : 201, static_cast<cudaStream_t>(stream_));
+  return launch_forward_vec(pr, dtype, vec_grid(pr, 3), (q_dtype == MSDA_BF16 ? 202 : q_dtype == MSDA_F16 ? 203 : 201), static_cast<cudaStream_t>(stream_));
 }
 
 int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -216,7 +219,7 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
   pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
-  void *acc = (dtype == MSDA_BF16) ? workspace : grad_value;
+  void *acc = is16(dtype) ? workspace : grad_value;
   pr.acc_permuted = acc_is_permuted(dtype, D, L);
   pr.grad_value_acc = acc;
   if (!(aligned16(value) && aligned16(sampling_offsets) && aligned16(attn_logits) && aligned16(reference_points) &&
@@ -224,17 +227,18 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
     return MSDA_E_UNSUPPORTED;
   const size_t n_value = (size_t)N * S * M * D;
   if (cudaError_t e = cudaMemsetAsync(acc, 0, n_value * 4, stream)) return (int)e;
-  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), q_dtype == MSDA_BF16 ? 202 : 201, stream);
+  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), (q_dtype == MSDA_BF16 ? 202 : q_dtype == MSDA_F16 ? 203 : 201), stream);
   if (rc != MSDA_OK) return rc;
-  if (dtype == MSDA_BF16)
-    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0, stream);
+  if (is16(dtype))
+    rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0,
+                            dtype == MSDA_F16, stream);
   return rc;
 }
 
 int msda_backward_finish_bf16(const void *workspace, void *grad_value, int N, int S, int M, int D, int L, void *stream_) {
   if (!workspace || !grad_value || N <= 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0) return MSDA_E_INVALID;
   return launch_f32_to_bf16(static_cast<const float *>(workspace), grad_value, (long long)N * S * M * D, D,
-                            acc_is_permuted(MSDA_BF16, D, L), static_cast<cudaStream_t>(stream_));
+                            acc_is_permuted(MSDA_BF16, D, L), false, static_cast<cudaStream_t>(stream_));
 }
 
 int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index, const float *sampling_loc,

@@ -292,12 +292,18 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
                 if (part == 0) go_[2 * o_p[t]] = gox;
                 if (part == (LPP > 1 ? 1 : 0)) go_[2 * o_p[t] + 1] = goy;
                 if (part == LPP - 1) gg_[o_p[t]] = glg;
-              } else {
+              } else if constexpr (PRE == 2) {
                 __nv_bfloat16 *go_ = static_cast<__nv_bfloat16 *>(pr.grad_loc) + lvl * (2 * P);
                 __nv_bfloat16 *gg_ = static_cast<__nv_bfloat16 *>(pr.grad_attn) + lvl * P;
                 if (part == 0) go_[2 * o_p[t]] = __float2bfloat16_rn(gox);
                 if (part == (LPP > 1 ? 1 : 0)) go_[2 * o_p[t] + 1] = __float2bfloat16_rn(goy);
                 if (part == LPP - 1) gg_[o_p[t]] = __float2bfloat16_rn(glg);
+              } else {
+                __half *go_ = static_cast<__half *>(pr.grad_loc) + lvl * (2 * P);
+                __half *gg_ = static_cast<__half *>(pr.grad_attn) + lvl * P;
+                if (part == 0) go_[2 * o_p[t]] = __float2half_rn(gox);
+                if (part == (LPP > 1 ? 1 : 0)) go_[2 * o_p[t] + 1] = __float2half_rn(goy);
+                if (part == LPP - 1) gg_[o_p[t]] = __float2half_rn(glg);
               }
             }
           }
@@ -312,6 +318,7 @@ static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
   if constexpr (D == 32 && P == 4) {
     if (minb == 201) { bwd_vec_kernel<VT, D, P, 2, 0, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
     if (minb == 202) { bwd_vec_kernel<VT, D, P, 2, 0, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 203) { bwd_vec_kernel<VT, D, P, 2, 0, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
     if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }   // ablations
     if (minb == 102) { bwd_vec_kernel<VT, D, P, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
   }
@@ -335,13 +342,14 @@ int launch_backward_vec(const Problem &pr, int dtype, int grid, int minb, cudaSt
   if (dtype == MSDA_F32 && pr.D >= 32) return dispatch_bwd<wide_f32>(pr, grid, minb, stream);   // 8 channels per lane
   if (dtype == MSDA_F32) return dispatch_bwd<float>(pr, grid, minb, stream);
   if (dtype == MSDA_BF16) return dispatch_bwd<__nv_bfloat16>(pr, grid, minb, stream);
+  if (dtype == MSDA_F16) return dispatch_bwd<__half>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;
 }
 
 // ---- fp32 accumulator -> bf16 ------------------------------------------------------------------
 // PERM: the accumulator rows use the permuted channel order of acc_pos() (bf16 value, D % 8 == 0).
 // One thread produces 8 consecutive bf16 channels (16 bytes) from two 16-byte accumulator chunks.
-template <bool PERM>
+template <bool PERM, typename HT>
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restrict__ src, uint4 *__restrict__ dst,
                                                          long long n8, int D) {
   const int lanes = D / 8;
@@ -358,34 +366,44 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
       a = *reinterpret_cast<const float4 *>(src + 8 * i);
       b = *reinterpret_cast<const float4 *>(src + 8 * i + 4);
     }
-    dst[i] = make_uint4(Chan<__nv_bfloat16>::pack2(a.x, a.y), Chan<__nv_bfloat16>::pack2(a.z, a.w),
-                        Chan<__nv_bfloat16>::pack2(b.x, b.y), Chan<__nv_bfloat16>::pack2(b.z, b.w));
+    dst[i] = make_uint4(Chan<HT>::pack2(a.x, a.y), Chan<HT>::pack2(a.z, a.w), Chan<HT>::pack2(b.x, b.y),
+                        Chan<HT>::pack2(b.z, b.w));
   }
 }
 
-__global__ void f32_to_bf16_scalar_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst,
-                                          long long first, long long n) {
+template <typename HT>
+__global__ void f32_to_bf16_scalar_kernel(const float *__restrict__ src, HT *__restrict__ dst, long long first,
+                                          long long n) {
   for (long long i = first + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16_rn(src[i]);
+       i += (long long)gridDim.x * blockDim.x) {
+    if constexpr (sizeof(HT) == 2 && !__is_same(HT, __half)) dst[i] = __float2bfloat16_rn(src[i]);
+    else dst[i] = __float2half_rn(src[i]);
+  }
 }
 
-int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, cudaStream_t stream) {
+template <typename HT>
+static int launch_narrow(const float *src, void *dst, long long n, int D, bool permuted, cudaStream_t stream) {
   const bool vec = (D % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) &&
                    ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
   if (vec) {
     const long long n8 = n / 8;
     const long long blocks = (n8 + 255) / 256;
     const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
-    if (permuted) f32_to_bf16_kernel<true><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
-    else f32_to_bf16_kernel<false><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
+    if (permuted) f32_to_bf16_kernel<true, HT><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
+    else f32_to_bf16_kernel<false, HT><<<grid, 256, 0, stream>>>(src, static_cast<uint4 *>(dst), n8, D);
   } else {
     if (permuted) return MSDA_E_UNSUPPORTED;
     const long long blocks = (n + 255) / 256;
     const int grid = (int)(blocks < 148LL * 16 ? blocks : 148LL * 16);
-    f32_to_bf16_scalar_kernel<<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16 *>(dst), 0, n);
+    f32_to_bf16_scalar_kernel<HT><<<grid, 256, 0, stream>>>(src, static_cast<HT *>(dst), 0, n);
   }
   return (int)cudaGetLastError();
+}
+
+// fp32 accumulator -> 16-bit grad_value (`half` selects fp16, otherwise bf16)
+int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, bool half, cudaStream_t stream) {
+  return half ? launch_narrow<__half>(src, dst, n, D, permuted, stream)
+              : launch_narrow<__nv_bfloat16>(src, dst, n, D, permuted, stream);
 }
 
 }  // namespace msda

@@ -13,6 +13,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -333,6 +334,30 @@ struct Chan<__nv_bfloat16> {
   }
   static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+};
+
+template <>
+struct Chan<__half> {
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw gather(const __half *p, bool pred) { return gather16(p, pred); }
+  static __device__ __forceinline__ Raw gather_plain(const __half *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+  static __device__ __forceinline__ void store(__half *p, const Raw &r) { *reinterpret_cast<uint4 *>(p) = r; }
+  static constexpr int kPerLane = 8;
+  static constexpr int kPairs = 4;
+  static __device__ __forceinline__ unsigned long long widen2(uint32_t w) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+    return pack_f2(f.x, f.y);
+  }
+  static __device__ __forceinline__ void unpack2(const uint4 &u, unsigned long long (&p)[4]) {
+    p[0] = widen2(u.x); p[1] = widen2(u.y); p[2] = widen2(u.z); p[3] = widen2(u.w);
+  }
+  static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<const uint32_t *>(&h);
   }
   static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {

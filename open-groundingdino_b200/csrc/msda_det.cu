@@ -31,8 +31,12 @@ template <typename VT>
 __device__ __forceinline__ float to_float(VT v) { return (float)v; }
 template <>
 __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
 template <typename CT, typename VT>
 __device__ __forceinline__ CT widen(VT v) { return (CT)v; }
+template <>
+__device__ __forceinline__ float widen<float, __half>(__half v) { return __half2float(v); }
 template <>
 __device__ __forceinline__ float widen<float, __nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
@@ -122,6 +126,9 @@ __device__ __forceinline__ VT from_double(double v) { return (VT)v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_double<__nv_bfloat16>(double v) { return __float2bfloat16_rn((float)v); }
 
+template <>
+__device__ __forceinline__ __half from_double<__half>(double v) { return __float2half_rn((float)v); }
+
 template <typename VT>
 __global__ void __launch_bounds__(256) det_finish_kernel(const Problem pr, const DetHeader *hdr,
                                                          const long long *__restrict__ acc, VT *__restrict__ out, long long n) {
@@ -164,6 +171,7 @@ int launch_backward_deterministic(const Problem &pr, int dtype, void *workspace,
   if ((reinterpret_cast<uintptr_t>(workspace) & 7u) != 0) return MSDA_E_INVALID;
   if (dtype == MSDA_F32) return run_det<float, float>(pr, workspace, stream);
   if (dtype == MSDA_BF16) return run_det<__nv_bfloat16, float>(pr, workspace, stream);
+  if (dtype == MSDA_F16) return run_det<__half, float>(pr, workspace, stream);
   if (dtype == MSDA_F64) return run_det<double, double>(pr, workspace, stream);
   return MSDA_E_UNSUPPORTED;
 }

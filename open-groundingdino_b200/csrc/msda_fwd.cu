@@ -132,6 +132,7 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
   if constexpr (D == 32 && P == 4) {
     if (minb == 201) { fwd_vec_kernel<VT, D, P, 3, PB3, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
     if (minb == 202) { fwd_vec_kernel<VT, D, P, 3, PB3, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 203) { fwd_vec_kernel<VT, D, P, 3, PB3, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
   }
   if (minb > 200) return MSDA_E_UNSUPPORTED;
   if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
@@ -150,7 +151,7 @@ static int dispatch_fwd(const Problem &pr, int grid, int minb, cudaStream_t stre
 }
 
 bool fwd_vec_supported(int dtype, int D, int P, int L) {
-  if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F16) return false;
   if (!(D == 16 || D == 32 || D == 64)) return false;
   if (!(P == 4 || P == 8)) return false;
   return L >= 1 && L <= kMaxLevels;
@@ -160,6 +161,7 @@ int launch_forward_vec(const Problem &pr, int dtype, int grid, int minb, cudaStr
   if (dtype == MSDA_F32 && pr.D >= 32) return dispatch_fwd<wide_f32>(pr, grid, minb, stream);   // 8 channels per lane
   if (dtype == MSDA_F32) return dispatch_fwd<float>(pr, grid, minb, stream);
   if (dtype == MSDA_BF16) return dispatch_fwd<__nv_bfloat16>(pr, grid, minb, stream);
+  if (dtype == MSDA_F16) return dispatch_fwd<__half>(pr, grid, minb, stream);
   return MSDA_E_UNSUPPORTED;
 }
 

@@ -17,6 +17,10 @@ template <>
 __device__ __forceinline__ float load_as<__nv_bfloat16, float>(const __nv_bfloat16 *p, long long i) {
   return __bfloat162float(p[i]);
 }
+template <>
+__device__ __forceinline__ float load_as<__half, float>(const __half *p, long long i) {
+  return __half2float(p[i]);
+}
 template <typename VT, typename CT>
 __device__ __forceinline__ void store_as(VT *p, long long i, CT v) {
   p[i] = (VT)v;
@@ -24,6 +28,11 @@ __device__ __forceinline__ void store_as(VT *p, long long i, CT v) {
 template <>
 __device__ __forceinline__ void store_as<__nv_bfloat16, float>(__nv_bfloat16 *p, long long i, float v) {
   p[i] = __float2bfloat16_rn(v);
+}
+
+template <>
+__device__ __forceinline__ void store_as<__half, float>(__half *p, long long i, float v) {
+  p[i] = __float2half_rn(v);
 }
 
 constexpr int kGenericThreads = 128;
@@ -141,6 +150,7 @@ int launch_forward_generic(const Problem &pr, int dtype, cudaStream_t stream) {
   if (dtype == MSDA_F32) fwd_generic_kernel<float, float><<<grid, kGenericThreads, 0, stream>>>(pr);
   else if (dtype == MSDA_F64) fwd_generic_kernel<double, double><<<grid, kGenericThreads, 0, stream>>>(pr);
   else if (dtype == MSDA_BF16) fwd_generic_kernel<__nv_bfloat16, float><<<grid, kGenericThreads, 0, stream>>>(pr);
+  else if (dtype == MSDA_F16) fwd_generic_kernel<__half, float><<<grid, kGenericThreads, 0, stream>>>(pr);
   else return MSDA_E_UNSUPPORTED;
   return (int)cudaGetLastError();
 }
@@ -150,6 +160,7 @@ int launch_backward_generic(const Problem &pr, int dtype, cudaStream_t stream) {
   if (dtype == MSDA_F32) bwd_generic_kernel<float, float><<<grid, kGenericThreads, 0, stream>>>(pr);
   else if (dtype == MSDA_F64) bwd_generic_kernel<double, double><<<grid, kGenericThreads, 0, stream>>>(pr);
   else if (dtype == MSDA_BF16) bwd_generic_kernel<__nv_bfloat16, float><<<grid, kGenericThreads, 0, stream>>>(pr);
+  else if (dtype == MSDA_F16) bwd_generic_kernel<__half, float><<<grid, kGenericThreads, 0, stream>>>(pr);
   else return MSDA_E_UNSUPPORTED;
   return (int)cudaGetLastError();
 }

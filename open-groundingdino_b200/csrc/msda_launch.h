@@ -17,7 +17,7 @@ int launch_forward_generic(const Problem &pr, int dtype, cudaStream_t stream);
 int launch_backward_generic(const Problem &pr, int dtype, cudaStream_t stream);
 
 // fp32 accumulator -> bf16 grad_value
-int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, cudaStream_t stream);
+int launch_f32_to_bf16(const float *src, void *dst, long long n, int D, bool permuted, bool half, cudaStream_t stream);
 
 // deterministic backward (two-pass)
 size_t deterministic_workspace_bytes(int N, int S, int M, int D, int L, int Lq, int P, int dtype);

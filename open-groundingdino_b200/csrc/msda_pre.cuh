@@ -4,7 +4,7 @@
 //          (MSDeformAttnFunction.apply, ops/functions/ms_deform_attn_func.py:23).
 // PRE = 1/2: the "next" row f1 of SURVEY.md section 8 -- the softmax over L*P and the location arithmetic of
 //          MSDeformAttn.forward (ops/modules/ms_deform_attn.py:98-108) are folded into the kernel prologue, so
-//          the kernel reads the raw sampling_offsets / attention logits (fp32: PRE 1, bf16: PRE 2) and the
+//          the kernel reads the raw sampling_offsets / attention logits (fp32: PRE 1, bf16: PRE 2, fp16: PRE 3) and the
 //          reference points, and neither `sampling_locations` nor `attention_weights` ever exists in HBM.
 //          Arithmetic mirrors the PyTorch expressions operation by operation so the pixel coordinates stay
 //          bit-identical to the unfused module:
@@ -30,8 +30,8 @@ __device__ __forceinline__ float round_like<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float round_like<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-template <int P, typename QT>
-__device__ __forceinline__ void load_q(const QT *p, bool act, float (&out)[P]);
+template <>
+__device__ __forceinline__ float round_like<__half>(float v) { return __half2float(__float2half_rn(v)); }
 
 // P floats
 template <int P>
@@ -55,6 +55,27 @@ __device__ __forceinline__ void load_q_bf16(const __nv_bfloat16 *p, bool act, fl
   }
 }
 
+// P fp16 values (P multiple of 4)
+template <int P>
+__device__ __forceinline__ void load_q_f16(const __half *p, bool act, float *out) {
+#pragma unroll
+  for (int v = 0; v < P / 4; ++v) {
+    uint2 u = make_uint2(0u, 0u);
+    if (act) u = __ldg(reinterpret_cast<const uint2 *>(p) + v);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    out[4 * v + 0] = a.x; out[4 * v + 1] = a.y; out[4 * v + 2] = b.x; out[4 * v + 3] = b.y;
+  }
+}
+
+// 16-bit quotient rounding of the PyTorch expression `half_or_bf16_tensor / int`
+template <int PRE>
+__device__ __forceinline__ float round_q(float v) {
+  if constexpr (PRE == 2) return round_like<__nv_bfloat16>(v);
+  else if constexpr (PRE == 3) return round_like<__half>(v);
+  else return v;
+}
+
 // Fills xy[2P] (normalised sampling positions) and a[P] (attention weights) of level `lc` of item `it`.
 // `span` = lanes that belong to the item (LPG * GI); all of them must call this together (shuffles).
 template <int P, int PRE>
@@ -70,9 +91,12 @@ __device__ __forceinline__ void level_inputs(const Problem &pr, const Item &it, 
     if constexpr (PRE == 1) {
       load_q_f32<2 * P>(static_cast<const float *>(pr.loc) + unit * (2 * P), act, off);
       load_q_f32<P>(static_cast<const float *>(pr.attn) + unit * P, act, lg);
-    } else {
+    } else if constexpr (PRE == 2) {
       load_q_bf16<2 * P>(static_cast<const __nv_bfloat16 *>(pr.loc) + unit * (2 * P), act, off);
       load_q_bf16<P>(static_cast<const __nv_bfloat16 *>(pr.attn) + unit * P, act, lg);
+    } else {
+      load_q_f16<2 * P>(static_cast<const __half *>(pr.loc) + unit * (2 * P), act, off);
+      load_q_f16<P>(static_cast<const __half *>(pr.attn) + unit * P, act, lg);
     }
     // reference point of (b, q, level): 2 or 4 floats
     const float *rp = pr.ref + ((long long)(it.b * pr.Lq + it.q) * pr.L + lc) * pr.ref_dim;
@@ -107,21 +131,15 @@ __device__ __forceinline__ void level_inputs(const Problem &pr, const Item &it, 
       const float fw = (float)W, fh = (float)H;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        if constexpr (PRE == 2) {
-          xy[2 * p] = __fadd_rn(rx, round_like<__nv_bfloat16>(__fdiv_rn(off[2 * p], fw)));
-          xy[2 * p + 1] = __fadd_rn(ry, round_like<__nv_bfloat16>(__fdiv_rn(off[2 * p + 1], fh)));
-        } else {
-          xy[2 * p] = __fadd_rn(rx, __fdiv_rn(off[2 * p], fw));
-          xy[2 * p + 1] = __fadd_rn(ry, __fdiv_rn(off[2 * p + 1], fh));
-        }
+        xy[2 * p] = __fadd_rn(rx, round_q<PRE>(__fdiv_rn(off[2 * p], fw)));
+        xy[2 * p + 1] = __fadd_rn(ry, round_q<PRE>(__fdiv_rn(off[2 * p + 1], fh)));
       }
       sc.mulx = sc.muly = 1.f; sc.divx = fw; sc.divy = fh;
     } else {
       const float fp = (float)P;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        float qx = __fdiv_rn(off[2 * p], fp), qy = __fdiv_rn(off[2 * p + 1], fp);
-        if constexpr (PRE == 2) { qx = round_like<__nv_bfloat16>(qx); qy = round_like<__nv_bfloat16>(qy); }
+        const float qx = round_q<PRE>(__fdiv_rn(off[2 * p], fp)), qy = round_q<PRE>(__fdiv_rn(off[2 * p + 1], fp));
         xy[2 * p] = __fadd_rn(rx, __fmul_rn(__fmul_rn(qx, rw), 0.5f));
         xy[2 * p + 1] = __fadd_rn(ry, __fmul_rn(__fmul_rn(qy, rh), 0.5f));
       }

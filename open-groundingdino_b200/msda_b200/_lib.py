@@ -11,7 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libmsda_b200.so")
 
-MSDA_F32, MSDA_BF16, MSDA_F64 = 0, 1, 2
+MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_F16 = 0, 1, 2, 3
 MSDA_BWD_ATOMIC, MSDA_BWD_DETERMINISTIC = 0, 1
 ABI_VERSION = 1
 VARIANT_NO_ZERO, VARIANT_NO_NARROW = 0x100, 0x200

@@ -6,9 +6,9 @@ error behaviour (RuntimeError for non-contiguous or CPU tensors, ops/src/cuda/ms
 28-38,52 and ms_deform_attn.h:38).  They validate, allocate outputs with torch, fetch the current
 CUDA stream and hand raw pointers to the C ABI (include/msda_b200.h).  Nothing is computed in Python.
 
-dtype contract: value fp32 (reference), fp64 (reference), or bf16 (new); sampling locations and
-attention weights are fp32 (fp64 with fp64 value) -- bf16/fp16 coordinates are widened, because a
-bf16 pixel coordinate is useless.
+dtype contract: value fp32 (reference), fp64 (reference), bf16 or fp16 (new, native 16-bit rows with fp32
+accumulation); sampling locations and attention weights are fp32 (fp64 with fp64 value) -- bf16/fp16
+coordinates are widened, because a 16-bit pixel coordinate is useless.
 """
 from __future__ import annotations
 
@@ -20,7 +20,8 @@ from torch.autograd.function import once_differentiable
 
 from . import _lib
 
-_DTYPE_CODE = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16, torch.float64: _lib.MSDA_F64}
+_DTYPE_CODE = {torch.float32: _lib.MSDA_F32, torch.bfloat16: _lib.MSDA_BF16, torch.float64: _lib.MSDA_F64,
+               torch.float16: _lib.MSDA_F16}
 
 # "atomic" (default) or "deterministic"; read per call so tests can flip it.
 _BWD_MODES = {"atomic": _lib.MSDA_BWD_ATOMIC, "deterministic": _lib.MSDA_BWD_DETERMINISTIC}
@@ -60,7 +61,7 @@ def _dims(value, spatial_shapes, sampling_loc, attn_weight):
 
 
 def _prepare(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
-    _require(value.dtype in _DTYPE_CODE, f"value dtype {value.dtype} not supported (fp32, fp64, bf16)")
+    _require(value.dtype in _DTYPE_CODE, f"value dtype {value.dtype} not supported (fp32, fp64, bf16, fp16)")
     coord_dtype = torch.float64 if value.dtype == torch.float64 else torch.float32
     if sampling_loc.dtype != coord_dtype:
         sampling_loc = sampling_loc.to(coord_dtype)
@@ -153,9 +154,9 @@ class MSDeformAttnFunction(Function):
 # ---- fused pre-op ----------------------------------------------------------
 def fused_supported(value, sampling_offsets, attn_logits, reference_points, n_levels, n_points) -> bool:
     """True when libmsda_b200 can take the raw offsets / logits directly (see include/msda_b200.h)."""
-    if not (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16)):
+    if not (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16, torch.float16)):
         return False
-    if sampling_offsets.dtype != attn_logits.dtype or sampling_offsets.dtype not in (torch.float32, torch.bfloat16):
+    if sampling_offsets.dtype != attn_logits.dtype or sampling_offsets.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         return False
     if reference_points.requires_grad or reference_points.shape[-1] not in (2, 4):
         return False

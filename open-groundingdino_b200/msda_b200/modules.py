@@ -51,6 +51,9 @@ class MSDeformAttn(nn.Module):
     #: fold softmax + sampling-location arithmetic into the kernels when the library supports the shape
     #:; False reproduces the reference's op-by-op graph (forward :98-124).
     fuse_pre_op = True
+    #: fp16 values (the reference's --amp mode) run on native fp16-row kernels instead of being widened to fp32 around
+    #: the op; False restores the reference's branch (:114-120) literally.
+    native_fp16 = True
 
     def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4):
         super().__init__()
@@ -104,7 +107,8 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
-        if (self.fuse_pre_op and value.is_contiguous() and offsets.is_contiguous() and weights.is_contiguous()
+        if (self.fuse_pre_op and (value.dtype != torch.float16 or self.native_fp16)
+                and value.is_contiguous() and offsets.is_contiguous() and weights.is_contiguous()
                 and fused_supported(value, offsets, weights, reference_points, self.n_levels, self.n_points)):
             out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, offsets, weights,
                                                   reference_points)
@@ -112,12 +116,13 @@ class MSDeformAttn(nn.Module):
         weights = F.softmax(weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         locations = sampling_locations_from(reference_points, offsets, input_spatial_shapes, self.n_points)
 
-        if value.dtype == torch.float16:
-            # the reference's AMP branch (:114-120): fp16 is widened around the op
+        if value.dtype == torch.float16 and not self.native_fp16:
+            # the reference's AMP branch verbatim (:114-120): fp16 is widened around the op
             out = MSDeformAttnFunction.apply(value.to(torch.float32), input_spatial_shapes, input_level_start_index,
                                              locations.to(torch.float32), weights, self.im2col_step)
             return self.output_proj(out.to(torch.float16))
-        # fp32 / fp64 as in the reference; bf16 value goes to the native bf16-value kernels
+        # fp32 / fp64 as in the reference; bf16 / fp16 values go to the native 16-bit-row kernels (same numbers as
+        # the widened path: the widening is exact, accumulation is fp32, the output is rounded once)
         out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, locations, weights,
                                          self.im2col_step)
         return self.output_proj(out)

@@ -20,17 +20,18 @@ def _unfused(value, sh, st, off, logit, ref, P):
     from msda_b200 import MSDeformAttnFunction
     from msda_b200.modules import sampling_locations_from
     N, Lq, M, L, _, _ = off.shape
-    aw = torch.softmax(logit.float() if logit.dtype == torch.bfloat16 else logit, -1).view(N, Lq, M, L, P)
+    aw = torch.softmax(logit.float(), -1).view(N, Lq, M, L, P)
     loc = sampling_locations_from(ref, off, sh, P)
     return MSDeformAttnFunction.apply(value, sh, st, loc, aw, 64), loc
 
 
 @pytest.mark.parametrize("ref_dim", [2, 4])
-@pytest.mark.parametrize("vdt,qdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("vdt,qdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float16, torch.float16), (torch.float16, torch.float32)])
 @pytest.mark.parametrize("encoder", [True, False])
 def test_fused_function_matches_unfused(ref_dim, vdt, qdt, encoder):
     from msda_b200.functions import MSDeformAttnFusedFunction, fused_supported
-    torch.manual_seed(ref_dim * 7 + (vdt == torch.bfloat16) + 2 * (qdt == torch.bfloat16))
+    torch.manual_seed(ref_dim * 7 + (vdt == torch.bfloat16) + 2 * (qdt == torch.bfloat16) + 4 * (vdt == torch.float16))
     sh, st = _tables(SHAPES)
     S = int(sh.prod(1).sum())
     N, M, D, L, P = 2, 8, 32, 4, 4
@@ -72,14 +73,14 @@ def test_fused_coordinates_bit_identical_to_pytorch_expression():
     sh, st = _tables(SHAPES)
     S = int(sh.prod(1).sum())
     N, M, D, L, P = 1, 8, 32, 4, 4
-    for qdt, ref_dim in ((torch.float32, 2), (torch.bfloat16, 2), (torch.float32, 4), (torch.bfloat16, 4)):
+    for qdt, ref_dim in ((torch.float32, 2), (torch.bfloat16, 2), (torch.float32, 4), (torch.bfloat16, 4), (torch.float16, 2), (torch.float16, 4)):
         value = torch.randn(N, S, M, D, device="cuda")
         off = (torch.randn(N, S, M, L, P, 2, device="cuda") * 2).to(qdt)
         logit = torch.zeros(N, S, M, L * P, device="cuda", dtype=qdt)
         ref = torch.rand(N, S, L, ref_dim, device="cuda")
         loc = sampling_locations_from(ref, off, sh, P).float().contiguous()
         aw = torch.full((N, S, M, L, P), 1.0 / (L * P), device="cuda")
-        v = value.to(torch.bfloat16) if qdt == torch.bfloat16 else value
+        v = value.to(qdt) if qdt != torch.float32 else value
         want = ms_deform_attn_forward(v, sh, st, loc, aw, 64)
         got = MSDeformAttnFusedFunction.apply(v, sh, st, off, logit, ref)
         # identical coordinates and exactly uniform weights => identical arithmetic => identical bits

@@ -221,3 +221,53 @@ def test_reference_gradcheck_fp64(channels):
     args = (value.double().requires_grad_(True), shapes, level_start_index,
             sampling_locations.double().requires_grad_(True), attention_weights.double().requires_grad_(True), 2)
     assert gradcheck(MSDeformAttnFunction.apply, args)
+
+
+def _fp16_round(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(torch.float16).float().numpy()
+
+
+@pytest.mark.parametrize("family", ["generic", "vec_linear"])
+@pytest.mark.parametrize("name", ["pyr4_wide_D32", "pyr5_P8_D16", "testpy_D64"])
+def test_golden_fp16_value(name, family):
+    """Native fp16 rows (the reference's --amp dtype): same contract as bf16 -- 16-bit value/grad, fp32 coordinates and
+    accumulation; tolerance 2e-3 (11-bit significand)."""
+    g = dict(load_golden(name))
+    g["value"] = _fp16_round(g["value"]); g["grad_out"] = _fp16_round(g["grad_out"])
+    args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
+    truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
+    res = run_cuda(g, torch.float16, FAMILIES[family])
+    check_all(g, res, truth, 2e-3)
+    assert_close("grad_attn_weight(fp32 part)", res[3], truth[3], 1e-5)
+
+
+def test_fp16_native_equals_reference_amp_branch():
+    """The reference widens fp16 around its fp32 op (modules/ms_deform_attn.py:114-120).  Widening is exact and both
+    paths accumulate in fp32 and round the output once, so the native fp16 kernels must give the same module output."""
+    import copy
+    from msda_b200 import MSDeformAttn
+    torch.manual_seed(11)
+    mod = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    shapes = [(16, 22), (8, 11), (4, 6), (2, 3)]
+    sh = torch.as_tensor(shapes, dtype=torch.long, device="cuda")
+    st = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    S = int(sh.prod(1).sum())
+    q = torch.randn(2, S, 256, device="cuda")
+    src = torch.randn(2, S, 256, device="cuda")
+    ref_pts = torch.rand(2, S, 4, 2, device="cuda")
+    outs = []
+    for native, fused in ((True, True), (True, False), (False, False)):
+        m = copy.deepcopy(mod)
+        m.native_fp16, m.fuse_pre_op = native, fused
+        x = src.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            o = m(q, ref_pts, x, sh, st)
+        assert o.dtype == torch.float16
+        (o.float().square().mean() * 4096.0).backward()     # loss scaling, as GradScaler would (fp16 grads underflow otherwise)
+        outs.append((o.detach().float().cpu().numpy(), x.grad.cpu().numpy()))
+    for o, gx in outs[:2]:
+        assert oracle.normwise(o, outs[2][0]) < 2e-3
+        assert oracle.normwise(gx, outs[2][1]) < 5e-3
