@@ -164,6 +164,48 @@ def fused_supported(value, sampling_offsets, attn_logits, reference_points, n_le
                                                 _DTYPE_CODE[sampling_offsets.dtype]))
 
 
+def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
+    """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D)."""
+    _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits),
+                   ("reference_points", reference_points)))
+    _require(reference_points.dtype == torch.float32, "reference_points must be fp32")
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_offsets.shape
+    with torch.cuda.device(value.device):
+        output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        rc = _lib.lib().msda_fused_forward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+            attention_logits.data_ptr(), reference_points.data_ptr(), output.data_ptr(), N, S, M, D, L, Lq, P,
+            reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], 0,
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "msda_fused_forward")
+    return output
+
+
+def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
+                   grad_output):
+    """-> (grad_value, grad_sampling_offsets, grad_attention_logits)"""
+    grad_output = grad_output.contiguous().to(value.dtype)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_offsets.shape
+    code = _DTYPE_CODE[value.dtype]
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)
+        grad_offsets = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attention_logits)
+        ws_bytes = _lib.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, _lib.MSDA_BWD_ATOMIC)
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
+        rc = _lib.lib().msda_fused_backward(
+            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+            attention_logits.data_ptr(), reference_points.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
+            grad_offsets.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, reference_points.shape[-1], code,
+            _DTYPE_CODE[sampling_offsets.dtype], 0, workspace.data_ptr() if workspace is not None else None, ws_bytes,
+            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "msda_fused_backward")
+    return grad_value, grad_offsets, grad_logits
+
+
 class MSDeformAttnFusedFunction(Function):
     """softmax + sampling-location arithmetic + multi-scale deformable attention in one kernel each way.
     forward(value (N,S,M,D), spatial_shapes, level_start_index, sampling_offsets (N,Lq,M,L,P,2),
@@ -172,18 +214,7 @@ class MSDeformAttnFusedFunction(Function):
     @staticmethod
     def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
         reference_points = reference_points.detach().to(torch.float32).contiguous()
-        _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
-                       ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits)))
-        N, S, M, D = value.shape
-        _, Lq, _, L, P, _ = sampling_offsets.shape
-        with torch.cuda.device(value.device):
-            output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-            rc = _lib.lib().msda_fused_forward(
-                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
-                attention_logits.data_ptr(), reference_points.data_ptr(), output.data_ptr(), N, S, M, D, L, Lq, P,
-                reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], 0,
-                torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "msda_fused_forward")
+        output = fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points)
         ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points)
         return output
 
@@ -191,21 +222,6 @@ class MSDeformAttnFusedFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points = ctx.saved_tensors
-        grad_output = grad_output.contiguous().to(value.dtype)
-        N, S, M, D = value.shape
-        _, Lq, _, L, P, _ = sampling_offsets.shape
-        code = _DTYPE_CODE[value.dtype]
-        with torch.cuda.device(value.device):
-            grad_value = torch.empty_like(value)
-            grad_offsets = torch.empty_like(sampling_offsets)
-            grad_logits = torch.empty_like(attention_logits)
-            ws_bytes = _lib.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, _lib.MSDA_BWD_ATOMIC)
-            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
-            rc = _lib.lib().msda_fused_backward(
-                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
-                attention_logits.data_ptr(), reference_points.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
-                grad_offsets.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, reference_points.shape[-1], code,
-                _DTYPE_CODE[sampling_offsets.dtype], 0, workspace.data_ptr() if workspace is not None else None, ws_bytes,
-                torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "msda_fused_backward")
+        grad_value, grad_offsets, grad_logits = fused_backward(value, spatial_shapes, level_start_index, sampling_offsets,
+                                                               attention_logits, reference_points, grad_output)
         return grad_value, None, None, grad_offsets, grad_logits, None

@@ -54,6 +54,9 @@ class MSDeformAttn(nn.Module):
     #: fp16 values (the reference's --amp mode) run on native fp16-row kernels instead of being widened to fp32 around
     #: the op; False restores the reference's branch (:114-120) literally.
     native_fp16 = True
+    #: call the kernels through torch.ops.msda_b200.* (msda_b200/torch_ops.py) so that selective activation
+    #: checkpointing can keep the op's output instead of recomputing it
+    use_dispatcher_ops = False
 
     def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4):
         super().__init__()
@@ -110,8 +113,13 @@ class MSDeformAttn(nn.Module):
         if (self.fuse_pre_op and (value.dtype != torch.float16 or self.native_fp16)
                 and value.is_contiguous() and offsets.is_contiguous() and weights.is_contiguous()
                 and fused_supported(value, offsets, weights, reference_points, self.n_levels, self.n_points)):
-            out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, offsets, weights,
-                                                  reference_points)
+            if self.use_dispatcher_ops:
+                from . import torch_ops  # noqa: F401  (registers torch.ops.msda_b200)
+                out = torch.ops.msda_b200.fused_forward(value, input_spatial_shapes, input_level_start_index, offsets,
+                                                        weights, reference_points.detach().float().contiguous())
+            else:
+                out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, offsets,
+                                                      weights, reference_points)
             return self.output_proj(out)
         weights = F.softmax(weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         locations = sampling_locations_from(reference_points, offsets, input_spatial_shapes, self.n_points)
@@ -123,8 +131,13 @@ class MSDeformAttn(nn.Module):
             return self.output_proj(out.to(torch.float16))
         # fp32 / fp64 as in the reference; bf16 / fp16 values go to the native 16-bit-row kernels (same numbers as
         # the widened path: the widening is exact, accumulation is fp32, the output is rounded once)
-        out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, locations, weights,
-                                         self.im2col_step)
+        if self.use_dispatcher_ops:
+            from . import torch_ops  # noqa: F401
+            out = torch.ops.msda_b200.forward(value, input_spatial_shapes, input_level_start_index,
+                                              locations.float().contiguous(), weights.float().contiguous(), self.im2col_step)
+        else:
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, locations, weights,
+                                             self.im2col_step)
         return self.output_proj(out)
 
 

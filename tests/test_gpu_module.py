@@ -258,3 +258,54 @@ def test_cuda_graph_capture_and_replay():
         assert torch.equal(out, want) and torch.equal(gl, wgl) and torch.equal(ga, wga)
         tol = 1e-5 if dt == torch.float32 else 1e-2
         assert oracle.normwise(gv.float().cpu().numpy(), wgv.float().cpu().numpy()) < tol
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_dispatcher_ops_and_selective_checkpoint(fused):
+    """torch.ops.msda_b200.* give the same numbers as the autograd.Function path, and a selective-checkpoint policy
+    that keeps the op's output skips its recomputation (scope row f3): the forward op runs once, not twice."""
+    import copy
+    from torch.utils.checkpoint import checkpoint, create_selective_checkpoint_contexts
+    from msda_b200 import MSDeformAttn, torch_ops
+    torch.manual_seed(21)
+    mod = MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.05)
+    mod.fuse_pre_op = fused
+    ref_mod = copy.deepcopy(mod)
+    mod.use_dispatcher_ops = True
+    sh, st = _tables(SHAPES)
+    S = int(sh.prod(1).sum())
+    q = torch.randn(2, S, 256, device="cuda")
+    src = torch.randn(2, S, 256, device="cuda")
+    ref_pts = torch.rand(2, S, 4, 2, device="cuda")
+
+    calls = {"n": 0}
+    name = "fused_forward" if fused else "forward"
+    from torch.utils._python_dispatch import TorchDispatchMode
+
+    class Count(TorchDispatchMode):
+        def __torch_dispatch__(self, func, types, args=(), kwargs=None):
+            if func is getattr(torch.ops.msda_b200, name).default:
+                calls["n"] += 1
+            return func(*args, **(kwargs or {}))
+
+    def run(m, ckpt):
+        x = src.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            if ckpt:
+                o = checkpoint(m, q, ref_pts, x, sh, st, use_reentrant=False,
+                               context_fn=lambda: create_selective_checkpoint_contexts(torch_ops.save_msda_policy))
+            else:
+                o = m(q, ref_pts, x, sh, st)
+        o.float().square().mean().backward()
+        return o.detach().float().cpu().numpy(), x.grad.cpu().numpy()
+
+    want = run(ref_mod, False)
+    got = run(mod, False)
+    with Count():
+        got_ckpt = run(mod, True)
+    assert calls["n"] == 1          # not recomputed in the backward
+    for a, b in ((got, want), (got_ckpt, want)):
+        assert oracle.normwise(a[0], b[0]) < 1e-6 and oracle.normwise(a[1], b[1]) < 2e-2

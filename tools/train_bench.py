@@ -37,14 +37,20 @@ class EncoderLayer(nn.Module):
 
 
 class Encoder(nn.Module):
-    def __init__(self, layers=6, use_checkpoint=False):
+    def __init__(self, layers=6, use_checkpoint=False, save_op_output=False):
         super().__init__()
         self.layers = nn.ModuleList(EncoderLayer() for _ in range(layers))
         self.use_checkpoint = use_checkpoint
+        self.save_op_output = save_op_output
 
     def forward(self, src, pos, ref, shapes, starts):
         for layer in self.layers:
-            if self.use_checkpoint:
+            if self.use_checkpoint and self.save_op_output:
+                from torch.utils.checkpoint import create_selective_checkpoint_contexts
+                from msda_b200.torch_ops import save_msda_policy
+                src = checkpoint(layer, src, pos, ref, shapes, starts, use_reentrant=False,
+                                 context_fn=lambda: create_selective_checkpoint_contexts(save_msda_policy))
+            elif self.use_checkpoint:
                 src = checkpoint(layer, src, pos, ref, shapes, starts, use_reentrant=False)
             else:
                 src = layer(src, pos, ref, shapes, starts)
@@ -107,6 +113,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per layer (config/cfg_odvg.py:42)")
+    ap.add_argument("--save-op-output", action="store_true",
+                    help="with --checkpoint: selective checkpointing that keeps the MSDeformAttn output (row f3)")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -115,7 +123,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     install_impl(a.impl)
     torch.manual_seed(1234)
-    model = Encoder(use_checkpoint=a.checkpoint).to(dev)
+    if a.save_op_output:
+        MSDeformAttn.use_dispatcher_ops = True
+    model = Encoder(use_checkpoint=a.checkpoint, save_op_output=a.save_op_output).to(dev)
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local])
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)
@@ -152,7 +162,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"impl": a.impl, "n_gpus": world, "batch_per_gpu": a.batch, "checkpoint": a.checkpoint,
+        print(json.dumps({"impl": a.impl, "n_gpus": world, "batch_per_gpu": a.batch, "checkpoint": a.checkpoint, "save_op_output": a.save_op_output,
                           "ms_per_step": float(t.item()), "images_per_s": world * a.batch / (float(t.item()) * 1e-3),
                           "loss": float(loss), "params": sum(p.numel() for p in model.parameters())}), flush=True)
     if world > 1:
