@@ -309,3 +309,49 @@ def test_dispatcher_ops_and_selective_checkpoint(fused):
     assert calls["n"] == 1          # not recomputed in the backward
     for a, b in ((got, want), (got_ckpt, want)):
         assert oracle.normwise(a[0], b[0]) < 1e-6 and oracle.normwise(a[1], b[1]) < 2e-2
+
+
+def test_concurrent_streams_are_independent():
+    """No global mutable state in the library: two problems running on two streams at once give the single-stream bits."""
+    from msda_b200 import ms_deform_attn_backward, ms_deform_attn_forward
+    gs = [make_inputs(SHAPES, N=2, M=8, D=32, Lq=None, P=4, dist="W", seed=50 + k) for k in range(2)]
+    dev = [{k: torch.from_numpy(g[k]).cuda() for k in ("value", "shapes", "starts", "loc", "attn", "grad_out")} for g in gs]
+    want = []
+    for d in dev:
+        o = ms_deform_attn_forward(d["value"], d["shapes"], d["starts"], d["loc"], d["attn"], 64)
+        gv, gl, ga = ms_deform_attn_backward(d["value"], d["shapes"], d["starts"], d["loc"], d["attn"], d["grad_out"], 64)
+        want.append((o, gl, ga, gv))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    got = [None, None]
+    for rep in range(3):
+        for k, (d, s) in enumerate(zip(dev, streams)):
+            with torch.cuda.stream(s):
+                o = ms_deform_attn_forward(d["value"], d["shapes"], d["starts"], d["loc"], d["attn"], 64)
+                gv, gl, ga = ms_deform_attn_backward(d["value"], d["shapes"], d["starts"], d["loc"], d["attn"], d["grad_out"], 64)
+                got[k] = (o, gl, ga, gv)
+        torch.cuda.synchronize()
+        for g_, w_ in zip(got, want):
+            assert torch.equal(g_[0], w_[0]) and torch.equal(g_[1], w_[1]) and torch.equal(g_[2], w_[2])
+            assert oracle.normwise(g_[3].cpu().numpy(), w_[3].cpu().numpy()) < 1e-5
+
+
+def test_large_batch_adjointness():
+    """bs 32 at the full encoder shape (the top of BASELINE.json's batch sweep): <fwd(v), g> == <v, grad_value(g)>."""
+    from msda_b200 import ms_deform_attn_backward, ms_deform_attn_forward
+    from helpers import SWIN_T_800x1333
+    torch.manual_seed(0)
+    sh, st = _tables(SWIN_T_800x1333)
+    S = int(sh.prod(1).sum())
+    N, M, D, L, P = 32, 8, 32, 4, 4
+    value = torch.randn(N, S, M, D, device="cuda", dtype=torch.bfloat16)
+    loc = torch.rand(N, S, M, L, P, 2, device="cuda")
+    attn = torch.softmax(torch.randn(N, S, M, L * P, device="cuda"), -1).view(N, S, M, L, P)
+    gout = torch.randn(N, S, M * D, device="cuda", dtype=torch.bfloat16)
+    out = ms_deform_attn_forward(value, sh, st, loc, attn, 64)
+    gv, gl, ga = ms_deform_attn_backward(value, sh, st, loc, attn, gout, 64)
+    lhs = (out.double() * gout.double()).sum().item()
+    rhs = (value.double() * gv.double()).sum().item()
+    scale = (out.double().abs() * gout.double().abs()).sum().item()
+    assert abs(lhs - rhs) < 2e-3 * scale ** 0.5 * 50 or abs(lhs - rhs) < 1e-4 * scale
+    assert abs((attn.double() * ga.double()).sum().item() - lhs) < 1e-4 * scale
