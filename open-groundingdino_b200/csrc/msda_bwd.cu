@@ -52,8 +52,11 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 }
 
 // ABL: ablation for profiling only (0 = the real kernel, 1 = reductions suppressed, 2 = value gathers suppressed)
-template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0>
-__global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr) {
+// SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
+template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0, bool SPEC = false>
+__global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr_in) {
+  Problem pr = pr_in;
+  if constexpr (SPEC) { pr.L = 4; pr.M = 8; }
   constexpr int CH = Chan<VT>::kPerLane;
   constexpr int NP = Chan<VT>::kPairs;
   constexpr int LPG = D / CH;
@@ -316,13 +319,25 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 template <typename VT, int D, int P>
 static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t stream) {
   if constexpr (D == 32 && P == 4) {
-    if (minb == 201) { bwd_vec_kernel<VT, D, P, 2, 0, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 202) { bwd_vec_kernel<VT, D, P, 2, 0, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 203) { bwd_vec_kernel<VT, D, P, 2, 0, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    const bool spec = pr.L == 4 && pr.M == 8;
+#define MSDA_FUSED(CODE, PREV)                                                                          \
+    if (minb == CODE) {                                                                                   \
+      if (spec) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true><<<grid, kThreads, 0, stream>>>(pr);           \
+      else bwd_vec_kernel<VT, D, P, 2, 0, PREV><<<grid, kThreads, 0, stream>>>(pr);                      \
+      return (int)cudaGetLastError();                                                                     \
+    }
+    MSDA_FUSED(201, 1) MSDA_FUSED(202, 2) MSDA_FUSED(203, 3)
+#undef MSDA_FUSED
     if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }   // ablations
     if (minb == 102) { bwd_vec_kernel<VT, D, P, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
   }
   if (minb >= 100) return MSDA_E_UNSUPPORTED;
+  if constexpr (D == 32 && P == 4) {
+    if (minb == 2 && pr.L == 4 && pr.M == 8) {
+      bwd_vec_kernel<VT, D, P, 2, 0, 0, true><<<grid, kThreads, 0, stream>>>(pr);
+      return (int)cudaGetLastError();
+    }
+  }
   if (minb == 4) bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
   else if (minb == 3) bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
   else bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);

@@ -22,8 +22,11 @@
 namespace msda {
 
 // PB = points whose 4 gathers are in flight together (register staging: PB*16 registers)
-template <typename VT, int D, int P, int MINB, int PB, int PRE = 0>
-__global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr) {
+// SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
+template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false>
+__global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr_in) {
+  Problem pr = pr_in;
+  if constexpr (SPEC) { pr.L = 4; pr.M = 8; }
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
   constexpr int NP = Chan<VT>::kPairs;     // fp32x2 accumulators per lane
   constexpr int LPG = D / CH;              // lanes per (item, level) group
@@ -130,11 +133,23 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
   constexpr int WR = sizeof(typename Chan<VT>::Raw) / 16;
   constexpr int PB2 = 4 / WR, PB3 = 2 / WR;
   if constexpr (D == 32 && P == 4) {
-    if (minb == 201) { fwd_vec_kernel<VT, D, P, 3, PB3, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 202) { fwd_vec_kernel<VT, D, P, 3, PB3, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 203) { fwd_vec_kernel<VT, D, P, 3, PB3, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    const bool spec = pr.L == 4 && pr.M == 8;
+#define MSDA_FUSED(CODE, PREV)                                                                          \
+    if (minb == CODE) {                                                                                   \
+      if (spec) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true><<<grid, kThreads, 0, stream>>>(pr);         \
+      else fwd_vec_kernel<VT, D, P, 3, PB3, PREV><<<grid, kThreads, 0, stream>>>(pr);                    \
+      return (int)cudaGetLastError();                                                                     \
+    }
+    MSDA_FUSED(201, 1) MSDA_FUSED(202, 2) MSDA_FUSED(203, 3)
+#undef MSDA_FUSED
   }
   if (minb > 200) return MSDA_E_UNSUPPORTED;
+  if constexpr (D == 32 && P == 4) {
+    if (minb == 3 && pr.L == 4 && pr.M == 8) {
+      fwd_vec_kernel<VT, D, P, 3, PB3, 0, true><<<grid, kThreads, 0, stream>>>(pr);
+      return (int)cudaGetLastError();
+    }
+  }
   if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
   else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, PB3><<<grid, kThreads, 0, stream>>>(pr);
   else fwd_vec_kernel<VT, D, P, 2, PB2><<<grid, kThreads, 0, stream>>>(pr);
