@@ -56,7 +56,7 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0, bool SPEC = false>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr_in) {
   Problem pr = pr_in;
-  if constexpr (SPEC) { pr.L = 4; pr.M = 8; }
+  if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; pr.acc_permuted = 0; }
   constexpr int CH = Chan<VT>::kPerLane;
   constexpr int NP = Chan<VT>::kPairs;
   constexpr int LPG = D / CH;

@@ -26,7 +26,7 @@ namespace msda {
 template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr_in) {
   Problem pr = pr_in;
-  if constexpr (SPEC) { pr.L = 4; pr.M = 8; }
+  if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; }
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
   constexpr int NP = Chan<VT>::kPairs;     // fp32x2 accumulators per lane
   constexpr int LPG = D / CH;              // lanes per (item, level) group
