@@ -398,6 +398,26 @@ def run_ours(args, cfg):
         lib.msda_host_destroy(c)
 
     extra = {}
+    if rank == 0 and args.dist == "I":
+        # transparency: the same kernels on the kernel-level worst case (uniform random sampling locations, no locality)
+        alt = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, "U", 900 + l, device), args.variant) for l in range(2)]
+        for lay in alt:
+            lay.forward(); lay.backward()
+        torch.cuda.synchronize()
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record()
+        for _ in range(3):
+            for lay in alt:
+                lay.forward()
+        a1.record()
+        for _ in range(3):
+            for lay in alt:
+                lay.backward()
+        a2.record()
+        torch.cuda.synchronize()
+        extra["distribution_U"] = {"ms_fwd_per_layer": a0.elapsed_time(a1) / 6, "ms_bwd_per_layer_incl_zero_and_narrow": a1.elapsed_time(a2) / 6,
+                                   "note": "uniform random sampling locations and random attention weights (SURVEY 8(d) distribution U)"}
+        del alt
     if rank == 0 and not args.no_ref_cuda:
         extra["reference_cuda_op"] = time_reference_cuda(torch, layers, cfg, ms_step)
         extra["reference_grid_sample_cuda"] = time_grid_sample_cuda(torch, layers, cfg, ms_step)
