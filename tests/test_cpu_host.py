@@ -115,3 +115,36 @@ def test_reference_arm_prints_one_schema_complete_json_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models/GroundingDINO/ops"), reason="reference tree not mounted")
+def test_reference_code_imports_against_the_shim():
+    """INTEGRATION.md route 1: with this repo's package directory on sys.path the reference's own
+    `import MultiScaleDeformableAttention as MSDA` (ops/functions/ms_deform_attn_func.py:18) resolves to the stand-in
+    module, and its unmodified MSDeformAttnFunction / MSDeformAttn run through it (on a CPU tensor that means the
+    reference's own 'Not implemented on the CPU' error, raised by our library binding)."""
+    import importlib
+    import sys
+    import types
+    sys.modules.pop("MultiScaleDeformableAttention", None)
+    ops = "/root/reference/models/GroundingDINO/ops"
+    pkg = types.ModuleType("refops")          # the ops directory as a package, without importing models/__init__
+    pkg.__path__ = [ops]
+    sys.modules["refops"] = pkg
+    try:
+        func = importlib.import_module("refops.functions.ms_deform_attn_func")
+        import MultiScaleDeformableAttention as shim
+        assert func.MSDA is shim and shim.__file__.startswith(os.path.join(ROOT, "open-groundingdino_b200"))
+        mod = importlib.import_module("refops.modules.ms_deform_attn").MSDeformAttn(64, 2, 2, 2)
+        sh = torch.tensor([[6, 4], [3, 2]])
+        st = torch.tensor([0, 24])
+        with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+            mod(torch.zeros(1, 5, 64), torch.rand(1, 5, 2, 2), torch.zeros(1, 30, 64), sh, st)
+        # and the reference module's parameters load into ours unchanged (same names, same shapes)
+        from msda_b200 import MSDeformAttn
+        ours = MSDeformAttn(64, 2, 2, 2)
+        ours.load_state_dict(mod.state_dict(), strict=True)
+        assert torch.equal(ours.sampling_offsets.bias, mod.sampling_offsets.bias)
+    finally:
+        for name in [k for k in sys.modules if k == "refops" or k.startswith("refops.")]:
+            sys.modules.pop(name)
