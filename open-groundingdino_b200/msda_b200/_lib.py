@@ -23,6 +23,8 @@ EXPORTS = (
     "msda_sample_index", "msda_host_create", "msda_host_destroy", "msda_host_h2d_bytes", "msda_host_d2h_bytes",
     "msda_host_fwd_bwd", "msda_host_submit", "msda_host_wait",
 )
+# include/hungarian_b200.h (the on-device Hungarian matcher, scope row f2)
+HM_EXPORTS = ("hm_max_columns", "hm_cost_matrix", "hm_assign", "hm_match")
 
 _lib = None
 
@@ -66,6 +68,15 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_host_submit.argtypes = [vp] * 11
     lib.msda_host_wait.restype = i
     lib.msda_host_wait.argtypes = [vp]
+    f = ctypes.c_float
+    lib.hm_max_columns.restype = i
+    lib.hm_max_columns.argtypes = []
+    lib.hm_cost_matrix.restype = i
+    lib.hm_cost_matrix.argtypes = [vp] * 6 + [i] * 3 + [f] * 4 + [vp]
+    lib.hm_assign.restype = i
+    lib.hm_assign.argtypes = [vp] * 5 + [i] * 3 + [vp]
+    lib.hm_match.restype = i
+    lib.hm_match.argtypes = [vp] * 9 + [i] * 4 + [f] * 4 + [vp]
 
 
 def lib() -> ctypes.CDLL:

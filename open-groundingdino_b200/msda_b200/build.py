@@ -15,6 +15,7 @@ def _sources():
     files = glob.glob(os.path.join(DIST_DIR, "csrc", "*.cu")) + glob.glob(os.path.join(DIST_DIR, "csrc", "*.cuh"))
     files += glob.glob(os.path.join(DIST_DIR, "csrc", "*.h"))
     files.append(os.path.join(os.path.dirname(DIST_DIR), "include", "msda_b200.h"))
+    files.append(os.path.join(os.path.dirname(DIST_DIR), "include", "hungarian_b200.h"))
     files.append(os.path.join(DIST_DIR, "build_lib.sh"))
     return files
 

@@ -28,6 +28,29 @@ def test_library_exports_every_declared_symbol():
     assert b"workspace" in _lib.lib().msda_error_string(-3)
 
 
+def test_matcher_header_symbols_exported_and_validated():
+    """include/hungarian_b200.h: every declared entry point is exported; rejected calls return before any CUDA work."""
+    from msda_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "hungarian_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(hm_[a-z0-9_]+)\s*\(", text)))
+    assert names == sorted(_lib.HM_EXPORTS)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), n
+    lib = _lib.lib()
+    assert lib.hm_max_columns() >= 900
+    assert lib.hm_cost_matrix(None, None, None, None, None, None, 1, 900, 256, 1.0, 1.0, 1.0, 0.25, None) == -1
+    assert lib.hm_assign(None, None, None, None, None, 1, 900, 10, None) == -1
+    assert lib.hm_assign(None, None, None, None, None, 0, 900, 10, None) == 0
+    assert lib.hm_cost_matrix(None, None, None, None, None, None, 1, 900, 4096, 1.0, 1.0, 1.0, 0.25, None) in (-1, -2)
+    import matcher_b200
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        matcher_b200.HungarianMatcher()({"pred_logits": torch.zeros(1, 4, 8), "pred_boxes": torch.zeros(1, 4, 4)},
+                                        [{"labels": torch.zeros(1, dtype=torch.int64), "boxes": torch.zeros(1, 4)}],
+                                        torch.ones(1, 8))
+
+
 def test_argument_validation_without_a_gpu():
     """Rejected calls return negative codes before any CUDA work is attempted."""
     from msda_b200 import _lib
