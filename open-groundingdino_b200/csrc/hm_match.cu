@@ -5,11 +5,12 @@
 //     (reference models/GroundingDINO/matcher.py:66-103, util/box_ops.py:9-14,25-62)   -> cost_kernel
 //   * `C.cpu()` + scipy.optimize.linear_sum_assignment per image (matcher.py:101,104-107) -> lsap_kernel
 //
-// cost_kernel: one warp per prediction row; lanes stride the K text tokens.  The focal terms of a row live in
-// registers; the targets' positive-map rows are normalised once per CTA into shared memory (32 targets at a time) and the
-// 32 x 2 dot products of a row are finished by one reduce-scatter (62 shuffles), which leaves lane t with target t's class
-// cost -- the same lane then adds that target's L1 and GIoU terms and stores 32 consecutive floats of the row.  The
-// arithmetic follows the PyTorch expressions operation by operation in fp32 (no contraction across the reference's ops).
+// cost_kernel: a CTA owns 64 prediction rows of one problem.  The targets' positive-map rows are normalised once per CTA
+// into shared memory (32 targets at a time) and their non-zero tokens compacted; a positive map marks the few tokens of
+// one phrase, so a (prediction, target) pair normally costs one thread a handful of exp/log evaluations plus the L1 and
+// GIoU terms (sparse path); wide rows fall back to one warp per prediction row with lane-strided dot products (dense
+// path).  The arithmetic follows the PyTorch expressions operation by operation in fp32 (no contraction across the
+// reference's ops).
 //
 // lsap_kernel: one CTA per problem runs the rectangular shortest-augmenting-path solver scipy uses (Crouse 2016), with
 // the reduced costs and dual variables in fp64 exactly as scipy computes them, so the result -- including the choice among
@@ -19,6 +20,7 @@
 // bandwidth-bound: what it buys is the removal of the device->host synchronisation, not throughput.
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <stdlib.h>
 #include <math_constants.h>
 #include <stdint.h>
 
@@ -29,28 +31,13 @@ namespace hm {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRowsPerCta = 32;      // prediction rows per CTA of the cost kernel
+constexpr int kRowsPerCta = 64;      // prediction rows per CTA of the cost kernel
 constexpr int kChunk = 32;           // targets normalised into shared memory at a time
 constexpr int kMaxColumns = 4096;    // max(Q, T) of the solver: 40 bytes of shared memory per column / row
 
 __device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fmaxf(a, b); }
 __device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? CUDART_NAN_F : fminf(a, b); }
 __device__ __forceinline__ float clamp0(float x) { return x < 0.f ? 0.f : x; }   // torch.clamp(min=0): NaN stays NaN
-
-// After the call lane t holds the sum over all lanes of a[t].
-__device__ __forceinline__ float reduce_scatter32(float (&a)[32], int lane) {
-#pragma unroll
-  for (int w = 16; w >= 1; w >>= 1) {
-    const bool upper = (lane & w) != 0;
-#pragma unroll
-    for (int i = 0; i < w; ++i) {
-      const float send = upper ? a[i] : a[i + w];
-      const float keep = upper ? a[i + w] : a[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-    }
-  }
-  return a[0];
-}
 
 // matcher.py:98 with box_ops.py:9-14 (cxcywh -> xyxy) and :25-62 (IoU, hull, GIoU), and :82 (L1 distance)
 __device__ __forceinline__ void box_costs(const float4 p, const float4 t, float &l1, float &giou) {
@@ -73,15 +60,43 @@ __device__ __forceinline__ void box_costs(const float4 p, const float4 t, float 
   giou = __fsub_rn(iou, __fdiv_rn(__fsub_rn(hull, uni), __fadd_rn(hull, 1e-6f)));
 }
 
-// KI = ceil(K / 32): tokens per lane
+// Focal class-cost terms of one logit (matcher.py:68,74-81), fp32 like the reference.
+__device__ __forceinline__ void focal_terms(float x, float alpha, float one_m_alpha, float &pos, float &neg) {
+  const float prob = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
+  const float one_m = __fsub_rn(1.f, prob);
+  neg = __fmul_rn(__fmul_rn(one_m_alpha, __fmul_rn(prob, prob)), -logf(__fadd_rn(one_m, 1e-8f)));
+  pos = __fmul_rn(__fmul_rn(alpha, __fmul_rn(one_m, one_m)), -logf(__fadd_rn(prob, 1e-8f)));
+}
+
+__device__ __forceinline__ float combine(float l1, float cls, float giou, float w_class, float w_bbox, float w_giou) {
+  float c = __fadd_rn(__fadd_rn(__fmul_rn(w_bbox, l1), __fmul_rn(w_class, cls)), __fmul_rn(w_giou, -giou));   // :100
+  if (c != c || fabsf(c) == CUDART_INF_F) c = 0.f;                                                             // :102-103
+  return c;
+}
+
+constexpr int kSparseCap = 16;   // non-zero tokens per positive-map row the sparse path keeps (a phrase is a few tokens)
+
+// KI = ceil(K / 32): tokens per lane.
+// Per chunk of 32 targets the CTA normalises the positive-map rows into shared memory and, while doing so, compacts
+// their non-zero tokens.  A positive map is a handful of ones per row (create_positive_map marks the tokens of one
+// phrase), so when every row of the chunk has at most kSparseCap non-zeros the class cost of a (prediction, target)
+// pair is evaluated by ONE thread from just those tokens -- exp/log are spent on ~T*nnz logits per prediction instead of
+// all K -- and the only pass over the full logits row is the NaN scan (a NaN logit anywhere in the row makes the
+// reference's dense product NaN, hence cost 0, for every target: NaN * 0 = NaN).  Otherwise the chunk takes the dense
+// path: one warp per prediction row, focal terms in registers, two lane-strided dot products per target.
 template <int KI>
-__global__ void __launch_bounds__(kThreads) cost_kernel(const float *__restrict__ logits, const float *__restrict__ pboxes,
+__global__ void __launch_bounds__(kThreads, KI <= 8 ? 4 : 2) cost_kernel(const float *__restrict__ logits, const float *__restrict__ pboxes,
                                                         const float *__restrict__ tboxes, const float *__restrict__ lmap,
                                                         const int4 *__restrict__ problems, float *__restrict__ cost, int Q,
                                                         int K, float w_class, float w_bbox, float w_giou, float alpha,
-                                                        float one_m_alpha) {
+                                                        float one_m_alpha, int force_dense) {
   extern __shared__ float smem[];          // kChunk x KP normalised positive-map rows (KP = 32 * KI, zero padded)
   constexpr int KP = 32 * KI;
+  __shared__ int sp_k[kChunk][kSparseCap];
+  __shared__ float sp_m[kChunk][kSparseCap];
+  __shared__ int sp_n[kChunk];             // non-zeros of the row; -1: the row holds NaN / inf (e.g. an all-zero map: 0/0)
+  __shared__ int row_nan[kRowsPerCta];
+  __shared__ int s_dense;
   const int4 pr = problems[blockIdx.y];
   const int t_first = pr.x, T = pr.y;
   if (T <= 0) return;
@@ -89,11 +104,39 @@ __global__ void __launch_bounds__(kThreads) cost_kernel(const float *__restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * kRowsPerCta;
 
+  // NaN scan of this CTA's prediction rows (the one full pass over the logits); all loads of a warp's rows are issued
+  // before the first vote so that they overlap
+  {
+    constexpr int RPW = kRowsPerCta / kWarps;
+    bool bad[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int q = q0 + warp + r * kWarps;
+      bad[r] = false;
+      if (q < Q) {
+        const float *row = logits + ((long long)blockIdx.y * Q + q) * K;
+#pragma unroll
+        for (int i = 0; i < KI; ++i) {
+          const int k = lane + 32 * i;
+          const float x = k < K ? __ldg(row + k) : 0.f;
+          bad[r] |= (x != x);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const unsigned any = __ballot_sync(0xffffffffu, bad[r]);
+      if (lane == 0) row_nan[warp + r * kWarps] = any != 0u;
+    }
+  }
+
   for (int c0 = 0; c0 < T; c0 += kChunk) {
     const int nt = min(kChunk, T - c0);
     __syncthreads();
-    // normalise this chunk's positive-map rows: row / row.sum()   (matcher.py:86-87)
-    for (int tt = warp; tt < kChunk; tt += kWarps) {
+    if (threadIdx.x == 0) s_dense = force_dense;
+    __syncthreads();
+    // normalise this chunk's positive-map rows: row / row.sum()   (matcher.py:86-87), and compact their non-zeros
+    for (int tt = warp; tt < nt; tt += kWarps) {
       float v[KI];
       float s = 0.f;
 #pragma unroll
@@ -104,29 +147,73 @@ __global__ void __launch_bounds__(kThreads) cost_kernel(const float *__restrict_
       }
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      int count = 0;
+      bool weird = false;
 #pragma unroll
-      for (int i = 0; i < KI; ++i) smem[tt * KP + lane + 32 * i] = (tt < nt && lane + 32 * i < K) ? __fdiv_rn(v[i], s) : 0.f;
+      for (int i = 0; i < KI; ++i) {
+        const int k = lane + 32 * i;
+        const float m = (tt < nt && k < K) ? __fdiv_rn(v[i], s) : 0.f;
+        smem[tt * KP + k] = m;
+        weird |= (m != m) || fabsf(m) == CUDART_INF_F;
+        const bool nz = m != 0.f;                       // NaN counts as non-zero, and marks the row below
+        const unsigned mask = __ballot_sync(0xffffffffu, nz);
+        const int at = count + __popc(mask & ((1u << lane) - 1u));
+        if (nz && at < kSparseCap) { sp_k[tt][at] = k; sp_m[tt][at] = m; }
+        count += __popc(mask);
+      }
+      const unsigned any_weird = __ballot_sync(0xffffffffu, weird);
+      if (lane == 0) {
+        sp_n[tt] = any_weird ? -1 : count;
+        if (!any_weird && count > kSparseCap) s_dense = 1;   // benign race: every writer stores 1
+      }
     }
     __syncthreads();
 
+    if (!s_dense) {
+      // ---- sparse path: one thread per (prediction, target) pair, targets fastest (coalesced stores) ----
+      for (int e = threadIdx.x; e < kRowsPerCta * nt; e += kThreads) {
+        const int qq = e / nt, tt = e - qq * nt;
+        const int q = q0 + qq;
+        if (q >= Q) break;
+        const long long row = (long long)blockIdx.y * Q + q;
+        const int n = sp_n[tt];
+        float cls;
+        if (n < 0 || row_nan[qq]) {
+          cls = CUDART_NAN_F;
+        } else {
+          float ap = 0.f, an = 0.f;
+          for (int z = 0; z < n; ++z) {
+            float pos, neg;
+            focal_terms(logits[row * K + sp_k[tt][z]], alpha, one_m_alpha, pos, neg);
+            const float m = sp_m[tt][z];
+            ap = fmaf(pos, m, ap);
+            an = fmaf(neg, m, an);
+          }
+          cls = __fsub_rn(ap, an);                                                 // pos @ m - neg @ m  (:88)
+        }
+        float l1, giou;
+        box_costs(*reinterpret_cast<const float4 *>(pboxes + row * 4),
+                  *reinterpret_cast<const float4 *>(tboxes + (long long)(t_first + c0 + tt) * 4), l1, giou);
+        block[(long long)q * T + c0 + tt] = combine(l1, cls, giou, w_class, w_bbox, w_giou);
+      }
+      continue;
+    }
+
+    // ---- dense path ----
     for (int qq = warp; qq < kRowsPerCta; qq += kWarps) {
       const int q = q0 + qq;
       if (q >= Q) break;                                   // warp-uniform
       const long long row = (long long)blockIdx.y * Q + q;
-      // focal terms of this prediction row (matcher.py:68,74-81), fp32 like the reference
       float pos[KI], neg[KI];
 #pragma unroll
       for (int i = 0; i < KI; ++i) {
         const int k = lane + 32 * i;
-        const float x = k < K ? logits[row * K + k] : 0.f;
-        const float prob = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x)));
-        const float one_m = __fsub_rn(1.f, prob);
-        neg[i] = __fmul_rn(__fmul_rn(one_m_alpha, __fmul_rn(prob, prob)), -logf(__fadd_rn(one_m, 1e-8f)));
-        pos[i] = __fmul_rn(__fmul_rn(alpha, __fmul_rn(one_m, one_m)), -logf(__fadd_rn(prob, 1e-8f)));
+        focal_terms(k < K ? logits[row * K + k] : 0.f, alpha, one_m_alpha, pos[i], neg[i]);
       }
-      float dp[32], dn[32];
-#pragma unroll
-      for (int tt = 0; tt < kChunk; ++tt) {
+      // one target at a time: two lane-strided dot products, each finished by a butterfly (this path is the rare one;
+      // keeping it free of per-target register arrays lets the kernel run 4 CTAs per SM)
+      float sp = 0.f, sn = 0.f;
+      for (int tt = 0; tt < nt; ++tt) {
         float ap = 0.f, an = 0.f;
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
@@ -134,19 +221,19 @@ __global__ void __launch_bounds__(kThreads) cost_kernel(const float *__restrict_
           ap = fmaf(pos[i], m, ap);
           an = fmaf(neg[i], m, an);
         }
-        dp[tt] = ap;
-        dn[tt] = an;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+          ap += __shfl_xor_sync(0xffffffffu, ap, d);
+          an += __shfl_xor_sync(0xffffffffu, an, d);
+        }
+        if (lane == tt) { sp = ap; sn = an; }
       }
-      const float sp = reduce_scatter32(dp, lane), sn = reduce_scatter32(dn, lane);
       if (lane < nt) {
         const int t = c0 + lane;
         float l1, giou;
         box_costs(*reinterpret_cast<const float4 *>(pboxes + row * 4),
                   *reinterpret_cast<const float4 *>(tboxes + (long long)(t_first + t) * 4), l1, giou);
-        const float cls = __fsub_rn(sp, sn);                                       // pos @ m - neg @ m  (:88)
-        float c = __fadd_rn(__fadd_rn(__fmul_rn(w_bbox, l1), __fmul_rn(w_class, cls)), __fmul_rn(w_giou, -giou));   // :100
-        if (c != c || fabsf(c) == CUDART_INF_F) c = 0.f;                           // :102-103
-        block[(long long)q * T + t] = c;
+        block[(long long)q * T + t] = combine(l1, __fsub_rn(sp, sn), giou, w_class, w_bbox, w_giou);
       }
     }
   }
@@ -169,10 +256,10 @@ __device__ __forceinline__ Best shfl_xor(const Best &b, int d) {
 
 __global__ void __launch_bounds__(kThreads) lsap_kernel(const float *__restrict__ cost, const int4 *__restrict__ problems,
                                                         long long *__restrict__ index_i, long long *__restrict__ index_j,
-                                                        int *__restrict__ status, int Q) {
+                                                        int *__restrict__ status, int Q, int stage_elems) {
   const int4 pr = problems[blockIdx.x];
   const int T = pr.y;
-  const float *__restrict__ C = cost + pr.z;
+  const float *C = cost + pr.z;
   long long *__restrict__ out_i = index_i + pr.w;
   long long *__restrict__ out_j = index_j + pr.w;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -192,6 +279,7 @@ __global__ void __launch_bounds__(kThreads) lsap_kernel(const float *__restrict_
   int *row4col = path + nc;
   int *remaining = row4col + nc;
   int *col4row = remaining + nc;             // nr
+  float *staged = reinterpret_cast<float *>(col4row + nr);   // the problem's cost block, when the host sized room for it
   __shared__ Best warp_best[kWarps];
   __shared__ int s_bad, s_i, s_sink, s_nrem;
   __shared__ double s_min;
@@ -202,12 +290,17 @@ __global__ void __launch_bounds__(kThreads) lsap_kernel(const float *__restrict_
   for (int r = tid; r < nr; r += kThreads) { u[r] = 0.0; col4row[r] = -1; }
   __syncthreads();
   {
+    // one pass over the block: the validity scan, and -- when it fits -- the copy into shared memory that takes the
+    // L2 round trip out of every Dijkstra step
+    const bool stage = (long long)Q * T <= (long long)stage_elems;
     int bad = 0;
     for (long long k = tid; k < (long long)Q * T; k += kThreads) {
       const float c = C[k];
       bad |= (c != c) || (c == -CUDART_INF_F);
+      if (stage) staged[k] = c;
     }
     if (bad) s_bad = 1;
+    if (stage) C = staged;
   }
   __syncthreads();
   int rc = s_bad ? -2 : 0;
@@ -315,10 +408,11 @@ __global__ void __launch_bounds__(kThreads) lsap_kernel(const float *__restrict_
   }
 }
 
-static size_t lsap_smem_bytes(int Q, int Tmax) {
+static size_t lsap_state_bytes(int Q, int Tmax) {
   const size_t nc = (size_t)(Q > Tmax ? Q : Tmax), nr = (size_t)(Q > Tmax ? Q : Tmax);   // either side may be the rows
   return nc * (8 + 8 + 4 + 4 + 4) + nr * (8 + 4) + 16;
 }
+constexpr size_t kLsapSmemBudget = 200 * 1024;
 
 }  // namespace hm
 
@@ -341,16 +435,17 @@ int hm_cost_matrix(const float *pred_logits, const float *pred_boxes, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid((Q + kRowsPerCta - 1) / kRowsPerCta, P);
   const int4 *pr = reinterpret_cast<const int4 *>(problems);
+  const int force_dense = getenv("HM_COST_DENSE") != nullptr;   // A/B switch for tests and profiling
   const float one_m_alpha = (float)(1.0 - (double)alpha);   // Python evaluates `1 - alpha` in double (matcher.py:80)
   if (K <= 256) {
     cost_kernel<8><<<grid, kThreads, kChunk * 256 * sizeof(float), st>>>(pred_logits, pred_boxes, tgt_boxes, tgt_label_map,
-                                                                          pr, cost, Q, K, w_class, w_bbox, w_giou, alpha, one_m_alpha);
+                                                                          pr, cost, Q, K, w_class, w_bbox, w_giou, alpha, one_m_alpha, force_dense);
   } else {
     const size_t bytes = kChunk * 1024 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(cost_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
     cost_kernel<32><<<grid, kThreads, bytes, st>>>(pred_logits, pred_boxes, tgt_boxes, tgt_label_map, pr, cost, Q, K,
-                                                   w_class, w_bbox, w_giou, alpha, one_m_alpha);
+                                                   w_class, w_bbox, w_giou, alpha, one_m_alpha, force_dense);
   }
   return (int)cudaGetLastError();
 }
@@ -361,14 +456,18 @@ int hm_assign(const float *cost, const int32_t *problems, int64_t *index_i, int6
   if (P == 0) return MSDA_OK;
   if (!problems || !status || (max_targets > 0 && (!cost || !index_i || !index_j))) return MSDA_E_INVALID;
   if (Q > kMaxColumns || max_targets > kMaxColumns) return MSDA_E_TOO_LARGE;
-  const size_t bytes = lsap_smem_bytes(Q, max_targets);
+  const size_t state = lsap_state_bytes(Q, max_targets);
+  // room for the largest cost block of the call next to the solver state, if the CTA's shared memory allows
+  const size_t block = (size_t)Q * (size_t)max_targets * sizeof(float);
+  const int stage_elems = state + block <= kLsapSmemBudget ? Q * max_targets : 0;
+  const size_t bytes = state + (stage_elems ? block : 0);
   if (bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
   }
   lsap_kernel<<<P, kThreads, bytes, static_cast<cudaStream_t>(stream)>>>(
       cost, reinterpret_cast<const int4 *>(problems), reinterpret_cast<long long *>(index_i),
-      reinterpret_cast<long long *>(index_j), status, Q);
+      reinterpret_cast<long long *>(index_j), status, Q, stage_elems);
   return (int)cudaGetLastError();
 }
 

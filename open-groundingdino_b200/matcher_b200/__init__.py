@@ -5,6 +5,6 @@ Mirrors models/GroundingDINO/matcher.py of PAVE-ComputerVision/Open-GroundingDin
   build_matcher      <- matcher.py:204-217
 The compute lives in libmsda_b200.so (C ABI, include/hungarian_b200.h); there is no CPU or scipy fallback.
 """
-from .matcher import HungarianMatcher, build_matcher, hungarian_assign, hungarian_match  # noqa: F401
+from .matcher import HungarianMatcher, build_matcher, hungarian_assign, hungarian_match, one_hot_targets  # noqa: F401
 
-__all__ = ["HungarianMatcher", "build_matcher", "hungarian_assign", "hungarian_match"]
+__all__ = ["HungarianMatcher", "build_matcher", "hungarian_assign", "hungarian_match", "one_hot_targets"]

@@ -75,7 +75,8 @@ def hungarian_match(pred_logits: torch.Tensor, pred_boxes: torch.Tensor, tgt_box
                           _ptr(index_j), _ptr(status), P, Q, K, t_max, float(cost_class), float(cost_bbox),
                           float(cost_giou), float(focal_alpha), stream)
     _lib.check(rc, "hm_match")
-    pairs = [(index_i[o:o + min(Q, t)], index_j[o:o + min(Q, t)]) for (_, t, _, o) in table]
+    counts = [min(Q, t) for (_, t, _, _) in table]
+    pairs = list(zip(index_i.split(counts), index_j.split(counts)))     # two calls instead of 2P slicing ops
     if return_cost:
         costs = [cost[c:c + Q * t].view(Q, t) for (_, t, c, _) in table]
         return pairs, costs, status
@@ -117,7 +118,7 @@ class HungarianMatcher(nn.Module):
     """Drop-in for the reference class of the same name (matcher.py:25-119): same constructor, same
     ``forward(outputs, targets, label_map)`` and the same return structure -- except that the index tensors live on the
     device of the predictions instead of the CPU (they are only ever used to index device tensors:
-    groundingdino.py:466-470,489-504).  ``match_sets`` is the batched form for a whole training step."""
+    groundingdino.py:444-446,504-514).  ``match_sets`` is the batched form for a whole training step."""
 
     def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha=0.25):
         super().__init__()
@@ -166,6 +167,19 @@ class HungarianMatcher(nn.Module):
         problems = [(firsts[b], sizes[b]) for _ in output_sets for b in range(bs)]
         flat = hungarian_match(logits, boxes, tgt_boxes, rows, problems, **self._weights())
         return [flat[s * bs:(s + 1) * bs] for s in range(len(output_sets))]
+
+
+def one_hot_targets(pairs, targets, label_maps, num_queries: int, num_tokens: int) -> torch.Tensor:
+    """The (bs, Q, K) int64 classification target the criterion builds from the matches on the host
+    (groundingdino.py:561-567: ``one_hot[i, indices[i][0]] = label_map_list[i][tgt_ids[i][indices[i][1]]]``), built on
+    the device from device index pairs -- index arithmetic only, no synchronisation."""
+    dev = pairs[0][0].device
+    one_hot = torch.zeros(len(pairs), num_queries, num_tokens, dtype=torch.int64, device=dev)
+    for b, (idx_i, idx_j) in enumerate(pairs):
+        if idx_i.numel():
+            rows = label_maps[b].to(dev)[targets[b]["labels"].to(dev)[idx_j]]
+            one_hot[b, idx_i] = rows.to(torch.int64)
+    return one_hot
 
 
 def build_matcher(args):

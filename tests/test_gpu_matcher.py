@@ -179,3 +179,84 @@ def test_edge_inputs_and_errors():
     class Args:
         matcher_type, set_cost_class, set_cost_bbox, set_cost_giou, focal_alpha = "HungarianMatcher", 1.0, 5.0, 2.0, 0.25
     assert isinstance(build_matcher(Args), HungarianMatcher)
+
+
+def _random_problem(gen, Q, K, T, n_cat, span):
+    lm = torch.zeros(n_cat, K)
+    for c in range(n_cat):
+        start = int(torch.randint(0, K - span, (1,), generator=gen))
+        lm[c, start:start + span] = torch.rand(span, generator=gen) + 0.1 if c % 2 else 1.0
+    labels = torch.randint(0, n_cat, (T,), generator=gen)
+    tb = torch.cat([torch.rand(T, 2, generator=gen), torch.rand(T, 2, generator=gen) * 0.4 + 0.02], -1)
+    logits = torch.randn(1, Q, K, generator=gen) * 2
+    pb = torch.cat([torch.rand(1, Q, 2, generator=gen), torch.rand(1, Q, 2, generator=gen) * 0.4 + 0.02], -1)
+    return logits, pb, tb, lm, labels
+
+
+@pytest.mark.parametrize("span,K,T", [(3, 256, 12), (16, 256, 40), (17, 256, 12), (60, 256, 33), (5, 100, 7), (40, 300, 9)])
+def test_cost_sparse_and_dense_paths(span, K, T, monkeypatch):
+    """Rows with <= 16 non-zero tokens take the per-pair sparse path, wider rows (or HM_COST_DENSE) the warp-per-row dense
+    path; both must reproduce the reference's fp32 cost within 1e-5 and give the oracle's pairs on their own matrix."""
+    from matcher_b200 import hungarian_match
+    dev = _dev()
+    gen = torch.Generator().manual_seed(100 + span)
+    Q = 300
+    logits, pb, tb, lm, labels = _random_problem(gen, Q, K, T, 6, span)
+    rows = lm[labels]
+    want = matcher_port.cost_matrix(logits[0], pb[0], tb, rows, 2.0, 5.0, 2.0, 0.25).numpy()
+    got = {}
+    for mode in ("auto", "dense"):
+        if mode == "dense":
+            monkeypatch.setenv("HM_COST_DENSE", "1")
+        pairs, costs, status = hungarian_match(logits.to(dev), pb.to(dev), tb.to(dev), rows.to(dev), [(0, T)],
+                                               cost_class=2.0, cost_bbox=5.0, cost_giou=2.0, return_cost=True)
+        c = costs[0].cpu().numpy()
+        assert np.abs(c.astype(np.float64) - want).max() / np.abs(want).max() <= COST_TOL, mode
+        _check_pairs(pairs[0], c, mode)
+        got[mode] = c
+    assert np.abs(got["auto"] - got["dense"]).max() <= 2e-6 * np.abs(want).max()
+
+
+def test_nan_logit_zeroes_the_whole_row_on_both_paths(monkeypatch):
+    """NaN * 0 = NaN in the reference's dense product: one NaN logit, even at a token no target uses, zeroes the row."""
+    from matcher_b200 import hungarian_match
+    dev = _dev()
+    gen = torch.Generator().manual_seed(9)
+    logits, pb, tb, lm, labels = _random_problem(gen, 40, 64, 6, 3, 2)
+    logits[0, 7, 63] = float("nan")
+    rows = lm[labels]
+    want = matcher_port.cost_matrix(logits[0], pb[0], tb, rows).numpy()
+    assert (want[7] == 0).all()
+    for mode in ("auto", "dense"):
+        if mode == "dense":
+            monkeypatch.setenv("HM_COST_DENSE", "1")
+        _, costs, _ = hungarian_match(logits.to(dev), pb.to(dev), tb.to(dev), rows.to(dev), [(0, 6)], return_cost=True)
+        c = costs[0].cpu().numpy()
+        assert (c[7] == 0).all() and np.abs(c - want).max() <= COST_TOL * np.abs(want).max()
+
+
+def test_one_hot_targets_equal_the_reference_host_loop():
+    """groundingdino.py:561-567 on the host vs the device builder, from the same matches."""
+    from matcher_b200 import HungarianMatcher, one_hot_targets
+    dev = _dev()
+    gen = torch.Generator().manual_seed(33)
+    bs, Q, K = 3, 120, 48
+    sizes = [5, 0, 9]
+    label_maps, targets = [], []
+    for t in sizes:
+        lm = torch.zeros(4, K)
+        for c in range(4):
+            lm[c, 2 + 5 * c:4 + 5 * c] = 1.0
+        label_maps.append(lm)
+        targets.append({"labels": torch.randint(0, 4, (t,), generator=gen).to(dev),
+                        "boxes": torch.cat([torch.rand(t, 2, generator=gen), torch.rand(t, 2, generator=gen) * 0.4 + 0.02], -1).to(dev)})
+    outputs = {"pred_logits": torch.randn(bs, Q, K, generator=gen).to(dev),
+               "pred_boxes": torch.cat([torch.rand(bs, Q, 2, generator=gen), torch.rand(bs, Q, 2, generator=gen) * 0.4 + 0.02], -1).to(dev)}
+    m = HungarianMatcher(2.0, 5.0, 2.0)
+    pairs = m.match_sets([outputs], targets, label_maps)[0]
+    got = one_hot_targets(pairs, targets, label_maps, Q, K)
+    want = torch.zeros(bs, Q, K, dtype=torch.int64)
+    for i in range(bs):                                   # the reference's loop, on the host
+        ids = targets[i]["labels"].cpu()[pairs[i][1].cpu()]
+        want[i, pairs[i][0].cpu()] = label_maps[i][ids].to(torch.long)
+    assert got.is_cuda and torch.equal(got.cpu(), want) and int(want.sum()) > 0
