@@ -64,6 +64,9 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   constexpr int NV = 4 * P;                       // dot products per (item, level)
   constexpr int C = NV >= LPG ? NV / LPG : 1;     // of which a lane owns C after the reduce-scatter
   constexpr bool COOP = (CH == 8 && LPG == 4);    // pairs of level groups send whole accumulator rows
+  // sliding-window aggregation of neighbour rows across the points of an (item, level): compiled into the kernels of the
+  // model's own geometry only -- in the generic variants its registers spill and cost 10-20 % on uniform inputs
+  constexpr bool WIN = SPEC;
 
   __shared__ Tables tb;
   load_tables(pr, tb);
@@ -110,10 +113,6 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
         float d[NV];
         float g_lh[P], g_lw[P], g_aw[P];
-        // pending grad_value contribution: consecutive points that fall into the same cell are summed
-        // in registers and sent as one set of reductions (warp-level aggregation before the L2 atomics)
-        float pend[4] = {0.f, 0.f, 0.f, 0.f};
-        int pend_off = 0, pend_mask = 0;
         // COOP (bf16, 4 lanes per row): two level groups of the same item pair up so that every reduction
         // instruction covers WHOLE 128-byte accumulator rows -- lanes of the first group send channels
         // [8j, 8j+4), lanes of the second [8j+4, 8j+8), first of the first group's row, then of the second's.
@@ -126,25 +125,26 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         const unsigned long long gsel1 = (COOP && !first) ? go[NP / 2 + 1] : go[1];
         float *gcoop = gacc + (long long)(it.b * pr.S) * MD + it.m * D + j * CH + (first ? 0 : 4);
         const int lvl_off = tb.start[lc] * MD;
-        auto flush = [&]() {
+        // one round of reductions of this group alone: coefficient e[kk] for the row at off + corner(kk); gslab-relative
+        auto plain_emit = [&](const float (&e)[4], int off, int wmd) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const int off = pend_off + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0);
-            if (ABL != 1 && ((pend_mask >> kk) & 1) && pend[kk] != 0.f) {
-              const unsigned long long c2 = pack_f2(pend[kk], pend[kk]);
+            const int o = off + ((kk & 1) ? MD : 0) + ((kk & 2) ? wmd : 0);
+            if (ABL != 1 && e[kk] != 0.f) {
+              const unsigned long long c2 = pack_f2(e[kk], e[kk]);
 #pragma unroll
               for (int h4 = 0; h4 < NP / 2; ++h4) {
                 float r0, r1, r2, r3;
                 unpack_f2(fmul2(c2, go[2 * h4]), r0, r1);
                 unpack_f2(fmul2(c2, go[2 * h4 + 1]), r2, r3);
-                red_add_f32x4(gslab + off + h4 * chunk_stride, r0, r1, r2, r3);
+                red_add_f32x4(gslab + o + h4 * chunk_stride, r0, r1, r2, r3);
               }
             }
           }
         };
-        // COOP: pending 2x2 window of neighbour-row coefficients (see the point loop)
+        // pending 2x2 window of neighbour-row coefficients (see the point loop)
         float win_c[4] = {0.f, 0.f, 0.f, 0.f};
-        int win_h = 0, win_w = 0, win_off = 0;
+        int win_h = 0, win_w = 0, win_off = 0, win_mask = 0;
         bool win_valid = false;
         // one round of pair-cooperative whole-row reductions: coefficient e[kk] for the row at off + corner(kk)
         auto coop_emit = [&](const float (&e)[4], int off, int wmd) {
@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             unpack_f2(dot2, dlo, dhi);
             d[4 * p + kk] = dlo + dhi;
           }
-          if (coop) {
+          if constexpr (WIN) {
             // Sliding 2x2 window over the points of this (item, level): neighbour rows that the next point's cell
             // shares with the current one (cells at most one pixel apart) are carried in registers and reduced
-            // once -- points of a head usually walk along a ray, a pixel or less apart on the coarser levels
-            // (default-init offsets: 26 % fewer reductions; uniform random locations: none, and no cost beyond
-            // ~40 ALU instructions per point).
+            // once -- warp-level aggregation before the L2 atomic units.  Points of a head usually walk along a
+            // ray, a pixel or less apart on the coarser levels (default-init offsets: 26 % fewer reductions;
+            // uniform random locations: none, at a cost of ~40 ALU instructions per point).
             const float ncw[4] = {(mask & 1) ? cw[0] : 0.f, (mask & 2) ? cw[1] : 0.f, (mask & 4) ? cw[2] : 0.f,
                                   (mask & 8) ? cw[3] : 0.f};
             const int dh = c.h_low - win_h, dw = c.w_low - win_w;
@@ -224,26 +224,41 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
               const bool r0 = near && dh <= 0, r1 = near && dh >= 0, c0 = dw <= 0, c1 = dw >= 0;
               const float e[4] = {(r0 && c0) ? 0.f : win_c[0], (r0 && c1) ? 0.f : win_c[1],
                                   (r1 && c0) ? 0.f : win_c[2], (r1 && c1) ? 0.f : win_c[3]};
-              coop_emit(e, win_off, WMD);
+              if (coop) coop_emit(e, lvl_off + win_off, WMD);
+              else plain_emit(e, win_off, WMD);
             }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) win_c[kk] = ncw[kk] + carry[kk];
-            win_h = c.h_low; win_w = c.w_low; win_valid = in; win_off = lvl_off + o00;
-          } else if (p > 0 && in && mask == pend_mask && o00 == pend_off) {
+            win_h = c.h_low; win_w = c.w_low; win_valid = in; win_off = o00;
+          } else if (coop) {
+            const float e[4] = {(mask & 1) ? cw[0] : 0.f, (mask & 2) ? cw[1] : 0.f, (mask & 4) ? cw[2] : 0.f,
+                                (mask & 8) ? cw[3] : 0.f};
+            coop_emit(e, lvl_off + o00, WMD);
+          } else if (p > 0 && in && mask == win_mask && o00 == win_off) {
             // same cell <=> same offset AND same neighbour mask: (h, W-1) and (h+1, -1) share the
-            // row-major offset but never the mask
+            // row-major offset but never the mask.  Consecutive points in one cell are summed in registers.
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) pend[kk] += cw[kk];
+            for (int kk = 0; kk < 4; ++kk) win_c[kk] += cw[kk];
           } else {
-            if (p > 0) flush();
+            if (p > 0) {
+              const float e[4] = {(win_mask & 1) ? win_c[0] : 0.f, (win_mask & 2) ? win_c[1] : 0.f,
+                                  (win_mask & 4) ? win_c[2] : 0.f, (win_mask & 8) ? win_c[3] : 0.f};
+              plain_emit(e, win_off, WMD);
+            }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) pend[kk] = cw[kk];
-            pend_off = o00;
-            pend_mask = mask;
+            for (int kk = 0; kk < 4; ++kk) win_c[kk] = cw[kk];
+            win_off = o00;
+            win_mask = mask;
           }
         }
-        if (coop) coop_emit(win_c, win_off, WMD);
-        else flush();
+        if constexpr (WIN) {
+          if (coop) coop_emit(win_c, lvl_off + win_off, WMD);
+          else plain_emit(win_c, win_off, WMD);
+        } else if (!coop) {
+          const float e[4] = {(win_mask & 1) ? win_c[0] : 0.f, (win_mask & 2) ? win_c[1] : 0.f,
+                              (win_mask & 4) ? win_c[2] : 0.f, (win_mask & 8) ? win_c[3] : 0.f};
+          plain_emit(e, win_off, WMD);
+        }
 
         reduce_scatter<NV, LPG / 2>(d, j);
 
