@@ -271,3 +271,40 @@ def test_fp16_native_equals_reference_amp_branch():
     for o, gx in outs[:2]:
         assert oracle.normwise(o, outs[2][0]) < 2e-3
         assert oracle.normwise(gx, outs[2][1]) < 5e-3
+
+
+@pytest.mark.parametrize("kind", ["jitter", "walk", "border", "repeat"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_aggregation_chains(kind, dtype):
+    """The model-geometry backward (L = 4, M = 8, D = 32, P = 4) carries neighbour rows shared by consecutive points in a
+    sliding 2x2 window.  Stress the carry logic: fractional chains in all eight directions (jitter), random unit walks
+    incl. diagonal and reversing steps (walk), chains that run across the image border (border), identical consecutive
+    points (repeat) -- against the fp64 oracle, atomic tiled and linear orders."""
+    rng = np.random.default_rng(77)
+    g = make_inputs(ENC_SMALL, N=2, M=8, D=32, Lq=None, P=4, dist="I", seed=8)
+    N, S, M, D, L, Lq, P = g["dims"]
+    wh = np.asarray([(w, h) for h, w in ENC_SMALL], dtype=np.float32)
+    if kind == "jitter":
+        g["loc"] = (g["loc"] + (rng.random(g["loc"].shape, dtype=np.float32) - 0.5) * 0.6 / wh[None, None, None, :, None, :]).astype(np.float32)
+    elif kind == "walk":
+        start = rng.random((N, Lq, M, L, 1, 2), dtype=np.float32)
+        steps = rng.integers(-1, 2, (N, Lq, M, L, P, 2)).astype(np.float32) * rng.choice([0.5, 1.0, 1.0, 2.0], (N, Lq, M, L, P, 1)).astype(np.float32)
+        g["loc"] = (start + np.cumsum(steps, axis=4) / wh[None, None, None, :, None, :]).astype(np.float32)
+    elif kind == "border":
+        edge = rng.choice([0.0, 1.0], (N, Lq, M, L, 1, 2)).astype(np.float32)
+        steps = (rng.random((N, Lq, M, L, P, 2), dtype=np.float32) - 0.5) * 2.5
+        g["loc"] = (edge + steps / wh[None, None, None, :, None, :]).astype(np.float32)
+    else:
+        g["loc"][:, :, :, :, 1] = g["loc"][:, :, :, :, 0]
+        g["loc"][:, :, :, :, 3] = g["loc"][:, :, :, :, 2]
+    logits = rng.standard_normal((N, Lq, M, L * P)).astype(np.float32)
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    g["attn"] = (e / e.sum(-1, keepdims=True)).reshape(N, Lq, M, L, P).astype(np.float32)
+    tol = FP32_TOL
+    if dtype == torch.bfloat16:
+        g["value"] = oracle.bf16_round(g["value"]); g["grad_out"] = oracle.bf16_round(g["grad_out"])
+        tol = BF16_TOL
+    truth_out = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
+    truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
+    for code in (2, 3):
+        check_all(g, run_cuda(g, dtype, code), truth, tol)
