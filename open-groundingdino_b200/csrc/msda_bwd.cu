@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
         float xy[2 * P], a[P];
         OffsetScale sc;
-        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, xy, a, sc);
+        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);
         const long long row_off = (long long)(it.b * pr.S + tb.start[lc]) * MD + it.m * D;
         const VT *slab = value + row_off + j * CH;
         // fp32 accumulator row of this head.  fp32 value: natural channel order (it IS grad_value).

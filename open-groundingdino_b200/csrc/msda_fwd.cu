@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         // (x,y) pairs and weights of this level (given, or derived from raw offsets/logits: msda_pre.cuh)
         float xy[2 * P], a[P];
         OffsetScale sc;
-        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, xy, a, sc);
+        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);
         const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
         const int WMD = W * MD;
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ float round_q(float v) {
 // `span` = lanes that belong to the item (LPG * GI); all of them must call this together (shuffles).
 template <int P, int PRE>
 __device__ __forceinline__ void level_inputs(const Problem &pr, const Item &it, int lc, bool act, int H, int W,
-                                             int LPG, int span, float (&xy)[2 * P], float (&a)[P], OffsetScale &sc) {
+                                             int LPG, int span, int j, float (&xy)[2 * P], float (&a)[P], OffsetScale &sc) {
   const long long unit = (long long)it.item * pr.L + lc;       // (item, level) index
   if constexpr (PRE == 0) {
     load_q_f32<2 * P>(static_cast<const float *>(pr.loc) + unit * (2 * P), act, xy);
@@ -109,6 +109,42 @@ __device__ __forceinline__ void level_inputs(const Problem &pr, const Item &it, 
         const float4 r = __ldg(reinterpret_cast<const float4 *>(rp));
         rx = r.x; ry = r.y; rw = r.z; rh = r.w;
       }
+    }
+    if (P == 4 && LPG == 4) {
+      // The four lanes of a group hold the same 4 points: lane j does point j's exp, its three IEEE divisions and its
+      // rounding, and the results are exchanged with 12 width-4 shuffles -- a quarter of the divisions per lane
+      // (the redundant prologue cost the fused kernels +37 % instructions over the plain ones).  Same operations on the
+      // same operands as the replicated form below, so coordinates stay bit-identical to the PyTorch expressions.
+      float m = -INFINITY;
+      if (act) m = fmaxf(fmaxf(lg[0], lg[1]), fmaxf(lg[2], lg[3]));
+      for (int d = LPG; d < span; d <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+      const float lgj = j == 0 ? lg[0] : (j == 1 ? lg[1] : (j == 2 ? lg[2] : lg[3]));
+      const float ox = j == 0 ? off[0] : (j == 1 ? off[2] : (j == 2 ? off[4] : off[6]));
+      const float oy = j == 0 ? off[1] : (j == 1 ? off[3] : (j == 2 ? off[5] : off[7]));
+      const float e = act ? expf(lgj - m) : 0.f;
+      float s = e;
+      for (int d = 1; d < span; d <<= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+      const float my_a = act ? __fdiv_rn(e, s) : 0.f;
+      float my_x, my_y;
+      if (pr.ref_dim == 2) {
+        const float fw = (float)W, fh = (float)H;
+        my_x = __fadd_rn(rx, round_q<PRE>(__fdiv_rn(ox, fw)));
+        my_y = __fadd_rn(ry, round_q<PRE>(__fdiv_rn(oy, fh)));
+        sc.mulx = sc.muly = 1.f; sc.divx = fw; sc.divy = fh;
+      } else {
+        const float fp = (float)P;
+        const float qx = round_q<PRE>(__fdiv_rn(ox, fp)), qy = round_q<PRE>(__fdiv_rn(oy, fp));
+        my_x = __fadd_rn(rx, __fmul_rn(__fmul_rn(qx, rw), 0.5f));
+        my_y = __fadd_rn(ry, __fmul_rn(__fmul_rn(qy, rh), 0.5f));
+        sc.mulx = 0.5f * rw; sc.muly = 0.5f * rh; sc.divx = sc.divy = fp;
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        a[p] = __shfl_sync(0xffffffffu, my_a, p, 4);
+        xy[2 * p] = __shfl_sync(0xffffffffu, my_x, p, 4);
+        xy[2 * p + 1] = __shfl_sync(0xffffffffu, my_y, p, 4);
+      }
+      return;
     }
     // softmax over the item's L*P logits: the item's groups hold one level each
     float m = -INFINITY;
