@@ -67,7 +67,7 @@ int vec_grid(const Problem &pr, int resident_per_sm) {
   // prologue runs once per CTA slot.  Capped by an upper bound of the unit count that needs no host
   // read of the (device-resident) shape table.
   const long long items = (long long)pr.N * pr.Lq * pr.M;
-  const long long upper = (items + kUnitItems - 1) / kUnitItems + (long long)pr.N * pr.M * 4 * pr.L + 64;
+  const long long upper = (items + 7) / 8 + (long long)pr.N * pr.M * 4 * pr.L + 64;   // >= units: the smallest unit is 8 items
   const long long want = (long long)sm_count() * resident_per_sm;
   return (int)(upper < want ? upper : want);
 }

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
   constexpr bool WIN = SPEC;
 
   __shared__ Tables tb;
-  load_tables(pr, tb);
+  load_tables(pr, tb, (kThreads / 32) * (G / min(G, pow2_ceil(pr.L))));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPG, j = lane % LPG;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
 
   for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
     const UnitCtx uc = decode_unit(pr, tb, unit);
-    for (int k0 = warp * IPW; k0 < kUnitItems; k0 += (kThreads / 32) * IPW) {
+    for (int k0 = warp * IPW; k0 < tb.unit_items; k0 += (kThreads / 32) * IPW) {
       const Item it = decode_item(pr, tb, uc, k0 + sub);
       const long long item = it.item;
 

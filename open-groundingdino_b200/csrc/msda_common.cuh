@@ -65,9 +65,13 @@ struct Tables {
   int n_tiles;                 // tiles per batch element (tiled order) -- 0 if tiling is off
   int n_items;                 // N * Lq * M
   int n_units;                 // work units in the whole launch
+  int unit_items;              // items per unit: kUnitItems for query tiles, one CTA pass in linear order
 };
 
-__device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb) {
+// linear_unit: items per unit when the queries are walked in their natural order -- one pass of the CTA's warps, so that
+// small launches (decoder: 57,600 items on 296-444 persistent CTAs) split into enough units to balance: with 64-item
+// units the last of 3 rounds ran 12 of 444 CTAs.
+__device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb, int linear_unit) {
   // one thread per level fetches its three int64 entries (independent loads, one round trip) ...
   if (threadIdx.x < pr.L) {
     const int l = threadIdx.x;
@@ -95,7 +99,8 @@ __device__ __forceinline__ void load_tables(const Problem &pr, Tables &tb) {
     const bool tiled = pr.tiled && area == (long long)pr.Lq;
     tb.n_tiles = tiled ? tiles : 0;
     tb.n_items = pr.N * pr.Lq * pr.M;      // < 2^31, checked by the host
-    tb.n_units = tiled ? pr.N * tiles * pr.M : (tb.n_items + kUnitItems - 1) / kUnitItems;
+    tb.unit_items = tiled ? kUnitItems : linear_unit;
+    tb.n_units = tiled ? pr.N * tiles * pr.M : (tb.n_items + linear_unit - 1) / linear_unit;
   }
   __syncthreads();
 }
@@ -138,12 +143,12 @@ __device__ __forceinline__ UnitCtx decode_unit(const Problem &pr, const Tables &
     uc.idx0 = 0;
   } else {
     uc.b = uc.m = uc.y0 = uc.x0 = uc.Hq = uc.Wq = uc.q0 = 0;
-    uc.idx0 = unit * kUnitItems;
+    uc.idx0 = unit * tb.unit_items;
   }
   return uc;
 }
 
-// k in [0, kUnitItems) -> item of the unit.
+// k in [0, tb.unit_items) -> item of the unit.
 __device__ __forceinline__ Item decode_item(const Problem &pr, const Tables &tb, const UnitCtx &uc, int k) {
   Item it;
   if (tb.n_tiles > 0) {
@@ -370,6 +375,20 @@ __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+
+// ---- cp.async staging of the per-item sampling positions / attention weights (model-geometry kernels) ----------------
+// Each warp copies the inputs of ITS items of the NEXT work unit into a private shared-memory slot while it works on the
+// current unit: the first use of the sampling positions was the longest single stall of both vector kernels (17 % of
+// the forward's stall samples, 10 % of the backward's).  Warp-private, so no block barrier enters the unit loop.
+constexpr int kStageItemFloats = 52;   // 32 position floats + 16 weights (+4 pad: the two items of a pass hit disjoint banks)
+constexpr int kStageSlots = 8;         // items of one unit handled by one warp (64 items / 8 warps)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ int pow2_ceil(int v) {
   int r = 1;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
   static_assert(D % CH == 0 && LPG >= 1 && LPG <= 32 && (LPG & (LPG - 1)) == 0, "unsupported head width");
 
   __shared__ Tables tb;
-  load_tables(pr, tb);
+  load_tables(pr, tb, (kThreads / 32) * (G / min(G, pow2_ceil(pr.L))));
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / LPG, j = lane % LPG;
@@ -47,9 +47,46 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
   VT *__restrict__ out = static_cast<VT *>(pr.out);
 
+  // model-geometry kernels: positions / weights of the next unit are staged by cp.async (msda_common.cuh)
+  constexpr bool STAGE = SPEC && PRE == 0 && P == 4 && G == 8;
+  __shared__ __align__(16) float stage[STAGE ? 2 * (kThreads / 32) * kStageSlots * kStageItemFloats : 4];
+  auto stage_slot = [&](int buf, int slot) {
+    return stage + ((buf * (kThreads / 32) + warp) * kStageSlots + slot) * kStageItemFloats;
+  };
+  auto stage_issue = [&](int u, int buf) {
+    const UnitCtx nu = decode_unit(pr, tb, u);
+    const int s = lane >> 2;                                             // slot = pass * IPW + sub
+    const int k = (s / IPW) * ((kThreads / 32) * IPW) + warp * IPW + (s % IPW);
+    const Item ni = decode_item(pr, tb, nu, k);
+    if (ni.valid && k < tb.unit_items) {
+      const float *gl = static_cast<const float *>(pr.loc) + (long long)ni.item * 32;
+      const float *ga = static_cast<const float *>(pr.attn) + (long long)ni.item * 16;
+      float *dst = stage_slot(buf, s);
+#pragma unroll
+      for (int t = 0; t < 3; ++t) {
+        const int c = (lane & 3) + 4 * t;                                // 12 chunks of 16 bytes per item
+        cp_async16(dst + c * 4, c < 8 ? gl + c * 4 : ga + (c - 8) * 4);
+      }
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if constexpr (STAGE) {
+    if ((int)blockIdx.x < tb.n_units) stage_issue(blockIdx.x, 0);
+  }
+
   for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
     const UnitCtx uc = decode_unit(pr, tb, unit);
-    for (int k0 = warp * IPW; k0 < kUnitItems; k0 += (kThreads / 32) * IPW) {
+    if constexpr (STAGE) {
+      if (unit + (int)gridDim.x < tb.n_units) {
+        stage_issue(unit + gridDim.x, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+    }
+    for (int k0 = warp * IPW; k0 < tb.unit_items; k0 += (kThreads / 32) * IPW) {
       const Item it = decode_item(pr, tb, uc, k0 + sub);
 
       unsigned long long acc[NP];
@@ -65,7 +102,12 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         // (x,y) pairs and weights of this level (given, or derived from raw offsets/logits: msda_pre.cuh)
         float xy[2 * P], a[P];
         OffsetScale sc;
-        level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);
+        if constexpr (STAGE) {
+          level_inputs_staged(stage_slot(buf, (k0 / ((kThreads / 32) * IPW)) * IPW + sub), lc, act, xy, a);
+          sc.mulx = sc.muly = sc.divx = sc.divy = 1.f;
+        } else {
+          level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);
+        }
         const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
         const int WMD = W * MD;
 
@@ -123,6 +165,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
       if (it.valid && gi == 0) {
         Chan<VT>::store(out + (long long)it.item * D + j * CH, Chan<VT>::pack(res));
       }
+    }
+    if constexpr (STAGE) {
+      __syncwarp();          // every lane is done with this buffer before the next unit's copies land in it
+      buf ^= 1;
     }
   }
 }
