@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         float xy[2 * P], a[P];
         OffsetScale sc;
         if constexpr (STAGE) {
-          level_inputs_staged(stage_slot(buf, (k0 / ((kThreads / 32) * IPW)) * IPW + sub), lc, act, xy, a);
+          level_inputs_staged(stage_slot(buf, (k0 / ((kThreads / 32) * IPW)) * IPW + sub), lc, xy, a);
           sc.mulx = sc.muly = sc.divx = sc.divy = 1.f;
         } else {
           level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);

@@ -76,14 +76,16 @@ __device__ __forceinline__ float round_q(float v) {
   else return v;
 }
 
-// PRE = 0 inputs of level `lc` from a staged item (kStageItemFloats floats: L*P (x,y) pairs, then L*P weights), P = 4
-__device__ __forceinline__ void level_inputs_staged(const float *sl, int lc, bool act, float (&xy)[8], float (&a)[4]) {
+// PRE = 0 inputs of level `lc` from a staged item (kStageItemFloats floats: L*P (x,y) pairs, then L*P weights), P = 4.
+// Slots of invalid items hold stale data: every use downstream is gated by `act && inside` (NaN / inf fail the inside
+// test, the gathers and reductions are predicated off), so nothing is zeroed here.
+__device__ __forceinline__ void level_inputs_staged(const float *sl, int lc, float (&xy)[8], float (&a)[4]) {
   const float4 p0 = *reinterpret_cast<const float4 *>(sl + lc * 8);
   const float4 p1 = *reinterpret_cast<const float4 *>(sl + lc * 8 + 4);
   const float4 w = *reinterpret_cast<const float4 *>(sl + 32 + lc * 4);
-  xy[0] = act ? p0.x : 0.f; xy[1] = act ? p0.y : 0.f; xy[2] = act ? p0.z : 0.f; xy[3] = act ? p0.w : 0.f;
-  xy[4] = act ? p1.x : 0.f; xy[5] = act ? p1.y : 0.f; xy[6] = act ? p1.z : 0.f; xy[7] = act ? p1.w : 0.f;
-  a[0] = act ? w.x : 0.f; a[1] = act ? w.y : 0.f; a[2] = act ? w.z : 0.f; a[3] = act ? w.w : 0.f;
+  xy[0] = p0.x; xy[1] = p0.y; xy[2] = p0.z; xy[3] = p0.w;
+  xy[4] = p1.x; xy[5] = p1.y; xy[6] = p1.z; xy[7] = p1.w;
+  a[0] = w.x; a[1] = w.y; a[2] = w.z; a[3] = w.w;
 }
 
 // Fills xy[2P] (normalised sampling positions) and a[P] (attention weights) of level `lc` of item `it`.
