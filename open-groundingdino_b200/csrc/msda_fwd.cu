@@ -23,7 +23,8 @@ namespace msda {
 
 // PB = points whose 4 gathers are in flight together (register staging: PB*16 registers)
 // SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
-template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false>
+// ST: stage the next unit's positions / weights with cp.async (model-geometry kernels in linear query order)
+template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false, bool ST = false>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr_in) {
   Problem pr = pr_in;
   if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; }
@@ -47,8 +48,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
   const VT *__restrict__ value = static_cast<const VT *>(pr.value);
   VT *__restrict__ out = static_cast<VT *>(pr.out);
 
-  // model-geometry kernels: positions / weights of the next unit are staged by cp.async (msda_common.cuh)
-  constexpr bool STAGE = SPEC && PRE == 0 && P == 4 && G == 8;
+  // positions / weights of the next unit are staged by cp.async (msda_common.cuh).  Launched for the linear query order
+  // only (decoder-like shapes, latency-bound: -9 %); in query-tile order the kernel is issue-bound and the ~6 % extra
+  // instructions cancel the shorter stalls (measured +0.5 %).
+  constexpr bool STAGE = ST && SPEC && PRE == 0 && P == 4 && G == 8;
   __shared__ __align__(16) float stage[STAGE ? 2 * (kThreads / 32) * kStageSlots * kStageItemFloats : 4];
   auto stage_slot = [&](int buf, int slot) {
     return stage + ((buf * (kThreads / 32) + warp) * kStageSlots + slot) * kStageItemFloats;
@@ -192,7 +195,8 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
   if (minb > 200) return MSDA_E_UNSUPPORTED;
   if constexpr (D == 32 && P == 4) {
     if (minb == 3 && pr.L == 4 && pr.M == 8) {
-      fwd_vec_kernel<VT, D, P, 3, PB3, 0, true><<<grid, kThreads, 0, stream>>>(pr);
+      if (pr.tiled) fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, false><<<grid, kThreads, 0, stream>>>(pr);
+      else fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, true><<<grid, kThreads, 0, stream>>>(pr);
       return (int)cudaGetLastError();
     }
   }
