@@ -171,6 +171,30 @@ __device__ __forceinline__ Item decode_item(const Problem &pr, const Tables &tb,
   return it;
 }
 
+// Work list of a persistent CTA.  Whole units are dealt round-robin; the units of the last, partial round are dealt
+// PASS by pass (a pass = the CTA's warps once over 8 * IPW items) so that the tail costs one pass instead of one unit:
+// 11,104 tile units on 444 CTAs are 25 full rounds plus 4 units -- without the split 440 CTAs idle for a whole unit.
+struct WorkItem {
+  int unit, pass_begin, pass_end;
+};
+__device__ __forceinline__ int work_count(const Tables &tb, int passes_per_unit) {
+  const int full = (tb.n_units / (int)gridDim.x) * (int)gridDim.x;
+  return full + (tb.n_units - full) * passes_per_unit;
+}
+__device__ __forceinline__ WorkItem work_item(const Tables &tb, int passes_per_unit, int w) {
+  const int full = (tb.n_units / (int)gridDim.x) * (int)gridDim.x;
+  WorkItem wi;
+  if (w < full) {
+    wi.unit = w; wi.pass_begin = 0; wi.pass_end = passes_per_unit;
+  } else {
+    const int t = w - full;
+    wi.unit = full + t / passes_per_unit;
+    wi.pass_begin = t % passes_per_unit;
+    wi.pass_end = wi.pass_begin + 1;
+  }
+  return wi;
+}
+
 // ---- sampler geometry --------------------------------------------------------------------------
 template <typename T>
 struct Cell {

@@ -78,9 +78,13 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
     if ((int)blockIdx.x < tb.n_units) stage_issue(blockIdx.x, 0);
   }
 
-  for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+  const int ppu = tb.unit_items / ((kThreads / 32) * IPW);     // passes per unit (1 in linear order)
+  const int n_work = work_count(tb, ppu);
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const WorkItem wi = work_item(tb, ppu, w);
+    const int unit = wi.unit;
     const UnitCtx uc = decode_unit(pr, tb, unit);
-    if constexpr (STAGE) {
+    if constexpr (STAGE) {                                     // linear order: one pass per unit, so w == unit
       if (unit + (int)gridDim.x < tb.n_units) {
         stage_issue(unit + gridDim.x, buf ^ 1);
         cp_async_wait<1>();
@@ -89,7 +93,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
       }
       __syncwarp();
     }
-    for (int k0 = warp * IPW; k0 < tb.unit_items; k0 += (kThreads / 32) * IPW) {
+    for (int pass = wi.pass_begin; pass < wi.pass_end; ++pass) {
+      const int k0 = warp * IPW + pass * (kThreads / 32) * IPW;
       const Item it = decode_item(pr, tb, uc, k0 + sub);
 
       unsigned long long acc[NP];
