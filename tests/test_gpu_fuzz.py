@@ -61,3 +61,45 @@ def test_random_shapes_all_families(case):
                 assert err <= tol, f"{name} dtype={dtype} variant={variant}: {err:.3e}"
             err = oracle.normwise(np.where(m, res[2], 0), np.where(m, tr[2], 0))
             assert err <= max(tol, 2e-5), f"grad_loc dtype={dtype} variant={variant}: {err:.3e}"
+
+
+def _spec_cases(n=12):
+    rng = np.random.default_rng(4242)
+    out = []
+    for i in range(n):
+        shapes = [(int(rng.integers(1, 40 >> l) + 1), int(rng.integers(1, 60 >> l) + 1)) for l in range(4)]
+        encoder = bool(rng.integers(0, 2))
+        Lq = None if encoder else int(rng.integers(1, 400))
+        out.append((i, shapes, int(rng.integers(1, 4)), Lq, str(rng.choice(["U", "W", "I"]))))
+    return out
+
+
+@pytest.mark.parametrize("case", _spec_cases(), ids=lambda c: f"{c[0]}-{'enc' if c[3] is None else 'q%d' % c[3]}-{c[4]}")
+def test_random_pyramids_model_geometry(case):
+    """The model's own geometry (L = 4, M = 8, D = 32, P = 4) selects the specialised kernels (window aggregation,
+    pass-wise tail, staged linear forward): random ragged pyramids, encoder and decoder query sets, all three input
+    distributions, both kernel orders, fp32 and bf16, against the fp64 oracle."""
+    from msda_b200 import functions as F
+    i, shapes, N, Lq, dist = case
+    g = make_inputs(shapes, N=N, M=8, D=32, Lq=Lq, P=4, dist=dist, seed=2000 + i)
+    if dist == "I":      # fractional chains: jitter the default-init rays
+        rng = np.random.default_rng(i)
+        wh = np.asarray([(w, h) for h, w in shapes], dtype=np.float32)
+        g["loc"] = (g["loc"] + (rng.random(g["loc"].shape, dtype=np.float32) - 0.5) * 0.8 / wh[None, None, None, :, None, :]).astype(np.float32)
+    m = generic_coordinate_mask(g["loc"], g["shapes"])
+    t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).cuda() if dt is None else torch.from_numpy(np.ascontiguousarray(a)).cuda().to(dt)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        v, go = (g["value"], g["grad_out"]) if dtype == torch.float32 else (oracle.bf16_round(g["value"]), oracle.bf16_round(g["grad_out"]))
+        args = (v, g["shapes"], g["starts"], g["loc"], g["attn"])
+        tr = (oracle.forward(*args, np.float64),) + oracle.backward(*args, go, np.float64)
+        value, gout = t(v, dtype), t(go, dtype)
+        sh, st, loc, attn = t(g["shapes"]), t(g["starts"]), t(g["loc"]), t(g["attn"])
+        for variant in (2, 3):
+            out = F.ms_deform_attn_forward(value, sh, st, loc, attn, 64, variant=variant)
+            gv, gl, ga = F.ms_deform_attn_backward(value, sh, st, loc, attn, gout, 64, variant=variant)
+            res = [x.double().cpu().numpy() for x in (out, gv, gl, ga)]
+            for name, got, want in zip(("output", "grad_value", "grad_attn"), (res[0], res[1], res[3]), (tr[0], tr[1], tr[3])):
+                err = oracle.normwise(got.reshape(want.shape), want)
+                assert err <= tol, f"{name} dtype={dtype} variant={variant}: {err:.3e}"
+            err = oracle.normwise(np.where(m, res[2], 0), np.where(m, tr[2], 0))
+            assert err <= max(tol, 2e-5), f"grad_loc dtype={dtype} variant={variant}: {err:.3e}"
