@@ -30,10 +30,11 @@
  *                                   offset of its pairs in index_i / index_j }
  *   cost           sum_p Q*T_p fp32 block p is the (Q, T_p) row-major matrix the reference calls c[i] (:105)
  *   index_i/_j     sum_p min(Q,T_p) int64: predictions (ascending) and their targets, scipy's (row_ind, col_ind)
- *   (environment: HM_COST_DENSE, if set, forces the warp-per-row dense path of the cost kernel -- an A/B switch for
- *    tests and profiling; results agree with the default sparse path to 2e-6 of the largest cost)
  *   status         (P) int32        0 = solved, -1 = infeasible (all remaining costs +inf), -2 = NaN or -inf entry
  *                                   (scipy raises ValueError for both; pairs are then filled with -1)
+ *
+ * Environment: HM_COST_DENSE, if set, forces the warp-per-row dense path of the cost kernel -- an A/B switch for tests
+ * and profiling; results agree with the default sparse path to 2e-6 of the largest cost.
  */
 #ifndef HUNGARIAN_B200_H_
 #define HUNGARIAN_B200_H_
