@@ -116,17 +116,23 @@ def hungarian_assign(cost_blocks: Sequence[torch.Tensor]):
 
 class HungarianMatcher(nn.Module):
     """Drop-in for the reference class of the same name (matcher.py:25-119): same constructor, same
-    ``forward(outputs, targets, label_map)`` and the same return structure -- except that the index tensors live on the
-    device of the predictions instead of the CPU (they are only ever used to index device tensors:
-    groundingdino.py:444-446,504-514).  ``match_sets`` is the batched form for a whole training step."""
+    ``forward(outputs, targets, label_map)`` and the same return structure.
 
-    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha=0.25):
+    ``indices_device``: the reference returns CPU index tensors (matcher.py:119) and its criterion indexes CPU tensors
+    with them (``tgt_ids[i][indices[i][1]]``, groundingdino.py:561-567), so the default "cpu" keeps the unmodified
+    criterion working -- at the price of ONE device->host read per call (instead of the reference's ~40 launches, the
+    cost-matrix copy and scipy).  ``None`` leaves them on the predictions' device: no synchronisation at all; use it
+    together with ``one_hot_targets`` / ``match_sets``."""
+
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha=0.25,
+                 indices_device="cpu"):
         super().__init__()
         self.cost_class = cost_class
         self.cost_bbox = cost_bbox
         self.cost_giou = cost_giou
         assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
         self.focal_alpha = focal_alpha
+        self.indices_device = indices_device
 
     def _weights(self):
         return dict(cost_class=self.cost_class, cost_bbox=self.cost_bbox, cost_giou=self.cost_giou,
@@ -146,13 +152,19 @@ class HungarianMatcher(nn.Module):
         for t in sizes:
             problems.append((first, t))
             first += t
-        return hungarian_match(logits, boxes, tgt_boxes, rows, problems, **self._weights())
+        pairs = hungarian_match(logits, boxes, tgt_boxes, rows, problems, **self._weights())
+        if self.indices_device is not None and torch.device(self.indices_device) != dev:
+            flat_i = torch.cat([p[0] for p in pairs]).to(self.indices_device)      # one copy for the whole call
+            flat_j = torch.cat([p[1] for p in pairs]).to(self.indices_device)
+            counts = [p[0].numel() for p in pairs]
+            pairs = list(zip(flat_i.split(counts), flat_j.split(counts)))
+        return pairs
 
     @torch.no_grad()
     def match_sets(self, output_sets, targets, label_maps):
         """All output sets of a step in one call.  ``output_sets``: list of dicts like ``outputs`` above (main, aux...,
         interm); ``label_maps``: one (num_categories_b, K) map per image (groundingdino.py:538-547).  Returns
-        ``result[s][b] = (index_i, index_j)``."""
+        ``result[s][b] = (index_i, index_j)``, always on the predictions' device (no synchronisation)."""
         dev = output_sets[0]["pred_logits"].device
         bs = len(targets)
         sizes = [len(v["boxes"]) for v in targets]
@@ -188,5 +200,6 @@ def build_matcher(args):
         "Unknown args.matcher_type: {}".format(args.matcher_type)
     if args.matcher_type == "HungarianMatcher":
         return HungarianMatcher(cost_class=args.set_cost_class, cost_bbox=args.set_cost_bbox,
-                                cost_giou=args.set_cost_giou, focal_alpha=args.focal_alpha)
+                                cost_giou=args.set_cost_giou, focal_alpha=args.focal_alpha,
+                                indices_device=getattr(args, "matcher_indices_device", "cpu"))
     raise NotImplementedError("matcher_b200 implements HungarianMatcher only (got {})".format(args.matcher_type))

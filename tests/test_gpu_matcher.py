@@ -93,7 +93,8 @@ def test_matcher_against_reference_golden(path):
     g = np.load(path)
     w = g["weights"]
     dev = _dev()
-    m = HungarianMatcher(cost_class=float(w[0]), cost_bbox=float(w[1]), cost_giou=float(w[2]), focal_alpha=float(g["focal_alpha"]))
+    m = HungarianMatcher(cost_class=float(w[0]), cost_bbox=float(w[1]), cost_giou=float(w[2]), focal_alpha=float(g["focal_alpha"]),
+                         indices_device=None)
     outputs = {"pred_logits": torch.from_numpy(g["pred_logits"])[None].to(dev), "pred_boxes": torch.from_numpy(g["pred_boxes"])[None].to(dev)}
     targets = [{"labels": torch.from_numpy(g["labels"]).to(dev), "boxes": torch.from_numpy(g["tgt_boxes"]).to(dev)}]
     label_map = torch.from_numpy(g["label_map"])               # on the CPU, like create_positive_map's output
@@ -134,7 +135,7 @@ def test_match_sets_equals_per_image_calls_and_oracle():
     output_sets = [{"pred_logits": (torch.randn(bs, Q, K, generator=gen) * 2).to(dev),
                     "pred_boxes": torch.cat([torch.rand(bs, Q, 2, generator=gen), torch.rand(bs, Q, 2, generator=gen) * 0.4 + 0.02], -1).to(dev)}
                    for _ in range(sets)]
-    m = HungarianMatcher(cost_class=2.0, cost_bbox=5.0, cost_giou=2.0)
+    m = HungarianMatcher(cost_class=2.0, cost_bbox=5.0, cost_giou=2.0, indices_device=None)
     got = m.match_sets(output_sets, targets, label_maps)
     assert len(got) == sets and all(len(g) == bs for g in got)
     for s in range(sets):
@@ -154,7 +155,7 @@ def test_match_sets_equals_per_image_calls_and_oracle():
 def test_edge_inputs_and_errors():
     from matcher_b200 import HungarianMatcher, build_matcher
     dev = _dev()
-    m = HungarianMatcher()
+    m = HungarianMatcher(indices_device=None)
     K, Q = 32, 50
     lm = torch.zeros(3, K)
     lm[0, 1:3] = 1
@@ -260,3 +261,29 @@ def test_one_hot_targets_equal_the_reference_host_loop():
         ids = targets[i]["labels"].cpu()[pairs[i][1].cpu()]
         want[i, pairs[i][0].cpu()] = label_maps[i][ids].to(torch.long)
     assert got.is_cuda and torch.equal(got.cpu(), want) and int(want.sum()) > 0
+
+
+def test_default_returns_cpu_indices_like_the_reference_and_its_host_loop_runs():
+    """Unmodified-criterion mode: CPU int64 index tensors (matcher.py:119), usable in the reference's host-side loop
+    (groundingdino.py:561-567) exactly as written there."""
+    from matcher_b200 import HungarianMatcher
+    dev = _dev()
+    gen = torch.Generator().manual_seed(12)
+    Q, K, T = 80, 40, 6
+    label_map = torch.zeros(3, K)
+    for c in range(3):
+        label_map[c, 2 + 4 * c:4 + 4 * c] = 1.0
+    targets = [{"labels": torch.randint(0, 3, (T,), generator=gen).to(dev),
+                "boxes": torch.cat([torch.rand(T, 2, generator=gen), torch.rand(T, 2, generator=gen) * 0.4 + 0.02], -1).to(dev)}]
+    outputs = {"pred_logits": torch.randn(1, Q, K, generator=gen).to(dev),
+               "pred_boxes": torch.cat([torch.rand(1, Q, 2, generator=gen), torch.rand(1, Q, 2, generator=gen) * 0.4 + 0.02], -1).to(dev)}
+    indices = HungarianMatcher(2.0, 5.0, 2.0)(outputs, targets, label_map)
+    assert all((not i.is_cuda) and i.dtype == torch.int64 and (not j.is_cuda) for i, j in indices)
+    same = HungarianMatcher(2.0, 5.0, 2.0, indices_device=None)(outputs, targets, label_map)
+    assert torch.equal(same[0][0].cpu(), indices[0][0]) and torch.equal(same[0][1].cpu(), indices[0][1])
+    one_hot = torch.zeros(1, Q, K, dtype=torch.int64)             # the reference's loop, verbatim in structure
+    tgt_ids = [v["labels"].cpu() for v in targets]
+    for i in range(len(indices)):
+        tgt_ids[i] = tgt_ids[i][indices[i][1]]
+        one_hot[i, indices[i][0]] = label_map[tgt_ids[i]].to(torch.long)
+    assert int(one_hot.sum()) == 2 * T
