@@ -475,6 +475,7 @@ int hm_match(const float *pred_logits, const float *pred_boxes, const float *tgt
              const int32_t *problems, float *cost, int64_t *index_i, int64_t *index_j, int32_t *status, int P, int Q, int K,
              int max_targets, float w_class, float w_bbox, float w_giou, float alpha, void *stream) {
   int rc = MSDA_OK;
+  if (max_targets > 0 && (!tgt_boxes || !tgt_label_map)) return MSDA_E_INVALID;   // some problem has targets
   if (max_targets > 0)
     rc = hm_cost_matrix(pred_logits, pred_boxes, tgt_boxes, tgt_label_map, problems, cost, P, Q, K, w_class, w_bbox, w_giou,
                         alpha, stream);

@@ -284,6 +284,7 @@ void msda_host_destroy(msda_host_ctx *c) {
 int msda_host_create(msda_host_ctx **out, int N, int S, int M, int D, int L, int Lq, int P, int dtype, int mode) {
   if (!out) return MSDA_E_INVALID;
   if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (mode != MSDA_BWD_ATOMIC && mode != MSDA_BWD_DETERMINISTIC) return MSDA_E_INVALID;
   msda_host_ctx *c = new (std::nothrow) msda_host_ctx();
   if (!c) return (int)cudaErrorMemoryAllocation;
   c->N = N; c->S = S; c->M = M; c->D = D; c->L = L; c->Lq = Lq; c->P = P; c->dtype = dtype; c->mode = mode;
@@ -331,7 +332,15 @@ int msda_host_submit(msda_host_ctx *c, const void *value, const int64_t *spatial
     return MSDA_E_INVALID;
   if (c->in_flight) return MSDA_E_INVALID;   // one submission per context at a time: wait first
   cudaError_t e;
-#define MSDA_TRY(x) if ((e = (x)) != cudaSuccess) return (int)e
+  // A failure after the first enqueue must not leave copies in flight that still reference the caller's host
+  // buffers (the caller is free to release them once this returns): drain the three streams first.
+  auto fail = [&](int rc) {
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->s_k);
+    cudaStreamSynchronize(c->s_out);
+    return rc;
+  };
+#define MSDA_TRY(x) if ((e = (x)) != cudaSuccess) return fail((int)e)
   // inputs (the previous use of the device input buffers ended with the previous wait)
   MSDA_TRY(cudaMemcpyAsync(c->d_shapes, spatial_shapes, c->b_shapes, cudaMemcpyHostToDevice, c->s_in));
   MSDA_TRY(cudaMemcpyAsync(c->d_starts, level_start_index, c->b_starts, cudaMemcpyHostToDevice, c->s_in));
@@ -344,12 +353,12 @@ int msda_host_submit(msda_host_ctx *c, const void *value, const int64_t *spatial
   MSDA_TRY(cudaStreamWaitEvent(c->s_k, c->e_in, 0));
   int rc = msda_forward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_out, c->N, c->S, c->M,
                         c->D, c->L, c->Lq, c->P, c->dtype, 0, c->s_k);
-  if (rc != MSDA_OK) return rc;
+  if (rc != MSDA_OK) return fail(rc);
   MSDA_TRY(cudaEventRecord(c->e_fwd, c->s_k));
   rc = msda_backward(c->d_value, c->d_shapes, c->d_starts, c->d_loc, c->d_attn, c->d_gout, c->d_gvalue,
                      c->d_gloc, c->d_gattn, c->N, c->S, c->M, c->D, c->L, c->Lq, c->P, c->dtype, c->mode, 0,
                      c->d_ws, c->b_ws, c->s_k);
-  if (rc != MSDA_OK) return rc;
+  if (rc != MSDA_OK) return fail(rc);
   MSDA_TRY(cudaEventRecord(c->e_bwd, c->s_k));
   // results: the output leaves while the backward runs
   MSDA_TRY(cudaStreamWaitEvent(c->s_out, c->e_fwd, 0));

@@ -5,8 +5,9 @@
 // associative instead of ordering it: contributions are converted to 64-bit fixed point and summed
 // with integer atomics (order-independent by construction), in two passes over grad_output:
 //   pass 1  max|grad_output| over the call  ->  a power-of-two scale 2^k such that no accumulator can
-//           overflow: every contribution is w_k * attn * g with w_k * attn <= 1, and one element of
-//           grad_value receives at most Lq * L * P of them, so |sum| <= max|g| * Lq * L * P < 2^(62-k).
+//           overflow: every contribution is w_k * attn * g with w_k <= 1, and one element of grad_value
+//           receives at most Lq * L * P of them, so |sum| <= max|g| * max(1, max|attn|) * Lq * L * P < 2^(62-k).
+//           (The op accepts any attention weights, not only softmax outputs, so max|attn| is measured too.)
 //   pass 2  the scatter of msda_generic.cu's backward with llrint(c * 2^k) added by RED.E.ADD.64;
 //           grad_sampling_loc / grad_attn_weight are written exactly as in the atomic mode (their
 //           channel sums are fixed-order shuffles there too, so they were already reproducible).
@@ -23,8 +24,9 @@ namespace msda {
 namespace {
 
 struct DetHeader {
-  unsigned max_bits;   // bit pattern of max|grad_output| (non-negative floats order like unsigned ints)
-  unsigned pad[63];
+  unsigned max_bits;        // bit pattern of max|grad_output| (non-negative floats order like unsigned ints)
+  unsigned max_attn_bits;   // bit pattern of max|attn_weight|
+  unsigned pad[62];
 };
 
 template <typename VT>
@@ -41,7 +43,7 @@ template <>
 __device__ __forceinline__ float widen<float, __nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 template <typename VT>
-__global__ void __launch_bounds__(256) det_max_kernel(const VT *__restrict__ g, long long n, DetHeader *hdr) {
+__global__ void __launch_bounds__(256) det_max_kernel(const VT *__restrict__ g, long long n, unsigned *slot) {
   float m = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
   {
@@ -50,12 +52,14 @@ __global__ void __launch_bounds__(256) det_max_kernel(const VT *__restrict__ g, 
     m = fmaxf(m, a);
   }
   for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0) atomicMax(&hdr->max_bits, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
 }
 
 // 2^k with k chosen from the header; identical in every thread of pass 2 and pass 3.
 __device__ __forceinline__ double det_scale(const DetHeader *hdr, const Problem &pr) {
-  const double bound = (double)__uint_as_float(hdr->max_bits) * (double)pr.Lq * (double)pr.L * (double)pr.P;
+  // 1.000001: the maxima were rounded to fp32 (fp64 inputs may sit half an ulp above them)
+  const double amax = fmax(1.0, (double)__uint_as_float(hdr->max_attn_bits));
+  const double bound = (double)__uint_as_float(hdr->max_bits) * amax * (double)pr.Lq * (double)pr.L * (double)pr.P * 1.000001;
   if (!(bound > 0.0) || !isfinite(bound)) return 1.0;
   int ex;
   frexp(bound, &ex);                 // bound < 2^ex
@@ -132,9 +136,9 @@ __device__ __forceinline__ __half from_double<__half>(double v) { return __float
 template <typename VT>
 __global__ void __launch_bounds__(256) det_finish_kernel(const Problem pr, const DetHeader *hdr,
                                                          const long long *__restrict__ acc, VT *__restrict__ out, long long n) {
-  const float mx = __uint_as_float(hdr->max_bits);
+  const float mx = __uint_as_float(hdr->max_bits), ma = __uint_as_float(hdr->max_attn_bits);
   const double inv = 1.0 / det_scale(hdr, pr);
-  const bool bad = !isfinite(mx);
+  const bool bad = !isfinite(mx) || !isfinite(ma);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = bad ? from_double<VT>(nan("")) : from_double<VT>((double)acc[i] * inv);
 }
@@ -148,7 +152,9 @@ int run_det(const Problem &pr, void *workspace, cudaStream_t stream) {
   if (cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(DetHeader) + (size_t)n_value * 8, stream)) return (int)e;
   const int cap = 148 * 16;
   auto grid_for = [&](long long n, int per) { long long b = (n + per - 1) / per; return (int)(b < cap ? b : cap); };
-  det_max_kernel<VT><<<grid_for(n_go, 256), 256, 0, stream>>>(static_cast<const VT *>(pr.grad_out), n_go, hdr);
+  det_max_kernel<VT><<<grid_for(n_go, 256), 256, 0, stream>>>(static_cast<const VT *>(pr.grad_out), n_go, &hdr->max_bits);
+  const long long n_attn = (long long)pr.N * pr.Lq * pr.M * pr.L * pr.P;
+  det_max_kernel<CT><<<grid_for(n_attn, 256), 256, 0, stream>>>(static_cast<const CT *>(pr.attn), n_attn, &hdr->max_attn_bits);
   const long long items = (long long)pr.N * pr.Lq * pr.M;
   const long long blocks = (items + 3) / 4;
   det_scatter_kernel<VT, CT><<<(int)(blocks < 148LL * 64 ? blocks : 148LL * 64), 128, 0, stream>>>(pr, hdr, acc);

@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
     if ((int)blockIdx.x < tb.n_units) stage_issue(blockIdx.x, 0);
   }
 
-  const int ppu = tb.unit_items / ((kThreads / 32) * IPW);     // passes per unit (1 in linear order)
+  // passes per unit (1 in linear order).  Rounded up: with 16 items per warp pass (16-bit rows, D = 16, L = 1) one pass
+  // of the 8 warps covers 128 > 64 items, and the items beyond the unit are masked below.
+  const int ipp = (kThreads / 32) * IPW;
+  const int ppu = (tb.unit_items + ipp - 1) / ipp;
   const int n_work = work_count(tb, ppu);
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const WorkItem wi = work_item(tb, ppu, w);
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
     }
     for (int pass = wi.pass_begin; pass < wi.pass_end; ++pass) {
       const int k0 = warp * IPW + pass * (kThreads / 32) * IPW;
-      const Item it = decode_item(pr, tb, uc, k0 + sub);
+      Item it = decode_item(pr, tb, uc, k0 + sub);
+      it.valid = it.valid && (k0 + sub < tb.unit_items);
 
       unsigned long long acc[NP];
 #pragma unroll

@@ -100,6 +100,7 @@ def hungarian_assign(cost_blocks: Sequence[torch.Tensor]):
         cost_off += Q * t
         pair_off += min(Q, t)
         t_max = max(t_max, t)
+    _require(cost_off < 2 ** 31, "cost matrices exceed 32-bit element offsets")
     lib = _lib.lib()
     _require(max(Q, t_max) <= lib.hm_max_columns(), f"max(Q, T) above {lib.hm_max_columns()} is not supported")
     cost = torch.cat([c.contiguous().view(-1) for c in cost_blocks]) if cost_off else torch.empty(0, device=dev)

@@ -16,7 +16,7 @@ MSDA_BWD_ATOMIC, MSDA_BWD_DETERMINISTIC = 0, 1
 ABI_VERSION = 1
 VARIANT_NO_ZERO, VARIANT_NO_NARROW = 0x100, 0x200
 
-# every symbol include/msda_b200.h declares (tests/test_cabi_symbols.py checks the two lists agree)
+# every symbol include/msda_b200.h declares (tests/test_cpu_host.py checks the two lists agree)
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
     "msda_backward_finish_bf16", "msda_fused_supported", "msda_fused_forward", "msda_fused_backward",

@@ -164,14 +164,35 @@ def fused_supported(value, sampling_offsets, attn_logits, reference_points, n_le
                                                 _DTYPE_CODE[sampling_offsets.dtype]))
 
 
-def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
-    """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D)."""
+def _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
+    """Shape / dtype validation of the fused entry points: a mismatch must be a RuntimeError, not an out-of-bounds
+    device read in the table prologue or the reference-point indexing."""
     _check_inputs((("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                    ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits),
                    ("reference_points", reference_points)))
+    _require(value.dtype in _DTYPE_CODE and sampling_offsets.dtype in _DTYPE_CODE, "unsupported dtype")
+    _require(sampling_offsets.dtype == attention_logits.dtype, "sampling_offsets and attention_logits must share a dtype")
     _require(reference_points.dtype == torch.float32, "reference_points must be fp32")
+    _require(spatial_shapes.dtype == torch.int64 and level_start_index.dtype == torch.int64,
+             "spatial_shapes and level_start_index must be int64")
+    _require(value.dim() == 4, "value must be (N, S, M, D)")
+    _require(sampling_offsets.dim() == 6 and sampling_offsets.size(5) == 2, "sampling_offsets must be (N, Lq, M, L, P, 2)")
     N, S, M, D = value.shape
     _, Lq, _, L, P, _ = sampling_offsets.shape
+    _require(tuple(sampling_offsets.shape) == (N, Lq, M, L, P, 2), "sampling_offsets does not match value")
+    _require(tuple(spatial_shapes.shape) == (L, 2) and level_start_index.numel() == L,
+             "spatial_shapes must be (L, 2) and level_start_index (L,) with L taken from sampling_offsets")
+    _require(attention_logits.numel() == N * Lq * M * L * P and attention_logits.size(0) == N,
+             "attention_logits must be (N, Lq, M, L*P)")
+    _require(reference_points.dim() == 4 and tuple(reference_points.shape[:3]) == (N, Lq, L)
+             and reference_points.shape[-1] in (2, 4), "reference_points must be (N, Lq, L, 2|4)")
+    return N, S, M, D, L, Lq, P
+
+
+def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
+    """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D)."""
+    N, S, M, D, L, Lq, P = _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits,
+                                       reference_points)
     with torch.cuda.device(value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
         rc = _lib.lib().msda_fused_forward(
@@ -187,8 +208,10 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
                    grad_output):
     """-> (grad_value, grad_sampling_offsets, grad_attention_logits)"""
     grad_output = grad_output.contiguous().to(value.dtype)
-    N, S, M, D = value.shape
-    _, Lq, _, L, P, _ = sampling_offsets.shape
+    N, S, M, D, L, Lq, P = _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits,
+                                       reference_points)
+    _check_inputs((("grad_output", grad_output),))
+    _require(grad_output.numel() == N * Lq * M * D, "grad_output must be (N, Lq, M*D)")
     code = _DTYPE_CODE[value.dtype]
     with torch.cuda.device(value.device):
         grad_value = torch.empty_like(value)

@@ -113,3 +113,66 @@ def test_module_fused_equals_module_unfused(autocast):
     tol = 3e-2 if autocast else 2e-5
     for got, want in zip(*outs):
         assert oracle.normwise(got.cpu().numpy(), want.cpu().numpy()) <= tol
+
+
+# ---- fused kernels against an INDEPENDENT judge ------------------------------------------------------------------
+# The tests above compare the fused path with this repo's own unfused path.  Here the judge is the grid_sample
+# formulation (oracle/torch_port.py, pinned to the reference by tests/golden) evaluated on the module's own PyTorch
+# expressions (ops/modules/ms_deform_attn.py:98-108) with autograd for the three gradients -- nothing of this repo's
+# CUDA is on the judge's side.  16-bit offsets / logits follow PyTorch's promotion rules (`bf16 / int64` stays bf16,
+# `fp32 + bf16` is fp32), exactly what the module would compute under autocast.
+def _judge(value, sh, shapes, off, logit, ref, P):
+    from oracle import torch_port
+    N, Lq, M, L, _, _ = off.shape
+    v = value.detach().float().requires_grad_(True)
+    o = off.detach().clone().requires_grad_(True)
+    lg = logit.detach().clone().requires_grad_(True)
+    aw = torch.softmax(lg.float(), -1).view(N, Lq, M, L, P)
+    if ref.shape[-1] == 2:
+        wh = torch.stack([sh[..., 1], sh[..., 0]], -1)
+        loc = ref[:, :, None, :, None, :] + o / wh[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + o / P * ref[:, :, None, :, None, 2:] * 0.5
+    out = torch_port.msda_grid_sample(v, shapes, loc.float(), aw)
+    return out, v, o, lg, loc.detach().float()
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("vdt,qdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32),
+                                     (torch.float16, torch.float16)])
+@pytest.mark.parametrize("encoder", [True, False])
+def test_fused_vs_grid_sample_port(ref_dim, vdt, qdt, encoder):
+    """PRE = 1/2/3 forward and backward, query-tile order (encoder=True: one query per pixel) and linear order."""
+    from conftest import generic_coordinate_mask
+    from msda_b200.functions import MSDeformAttnFusedFunction
+    torch.manual_seed(100 + ref_dim + 3 * (vdt == torch.bfloat16) + 5 * (qdt == torch.bfloat16) + 7 * encoder)
+    shapes = [(24, 37), (12, 19), (6, 10), (3, 5)]
+    sh, st = _tables(shapes)
+    S = int(sh.prod(1).sum())
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    Lq = S if encoder else 131
+    value = torch.randn(N, S, M, D, device="cuda").to(vdt)
+    off = (torch.randn(N, Lq, M, L, P, 2, device="cuda") * 2.5).to(qdt)
+    logit = torch.randn(N, Lq, M, L * P, device="cuda").to(qdt)
+    ref = torch.rand(N, Lq, L, ref_dim, device="cuda")
+    if ref_dim == 4:
+        ref[..., 2:] = ref[..., 2:] * 0.3 + 0.02
+    gout = torch.randn(N, Lq, M * D, device="cuda").to(vdt)
+
+    want_out, jv, jo, jl, loc = _judge(value, sh, shapes, off, logit, ref, P)
+    want_out.backward(gout.float())
+    b = [t.detach().clone().requires_grad_(True) for t in (value, off, logit)]
+    got = MSDeformAttnFusedFunction.apply(b[0], sh, st, b[1], b[2], ref)
+    got.backward(gout)
+    torch.cuda.synchronize()
+
+    tol = 1e-5 if vdt == torch.float32 else (1e-2 if vdt == torch.bfloat16 else 2e-3)
+    qtol = 2e-5 if qdt == torch.float32 else (2e-2 if qdt == torch.bfloat16 else 4e-3)   # gradients stored in qdt
+    n = lambda x, y: oracle.normwise(x.detach().double().cpu().numpy(), y.detach().double().cpu().numpy())
+    assert n(got, want_out) <= tol, "output"
+    assert n(b[0].grad, jv.grad) <= tol, "grad_value"
+    assert n(b[2].grad, jl.grad) <= qtol, "grad_attention_logits"
+    # grad wrt offsets is discontinuous at integer pixel coordinates and grid_sample rounds its coordinates differently
+    # (SURVEY.md 7.3): compare where the sample is farther than 1e-4 px from an integer coordinate
+    m = torch.from_numpy(np.ascontiguousarray(generic_coordinate_mask(loc.cpu().numpy(), np.asarray(shapes)))).cuda()
+    assert n(torch.where(m, b[1].grad.float(), 0.0), torch.where(m, jo.grad.float(), 0.0)) <= qtol, "grad_sampling_offsets"

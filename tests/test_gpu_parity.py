@@ -308,3 +308,44 @@ def test_window_aggregation_chains(kind, dtype):
     truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
     for code in (2, 3):
         check_all(g, run_cuda(g, dtype, code), truth, tol)
+
+
+@pytest.mark.parametrize("variant", [0, 3])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_single_level_narrow_heads_16bit_encoder(dtype, variant):
+    """16-bit rows with D = 16 and ONE level in query-tile order: a warp pass covers 16 items, so one pass of the 8 warps
+    is 128 items -- more than the 64 of a unit.  The forward's pass count used to round down to 0 there and return an
+    uninitialised output with rc 0 (round-1 advisor finding); the sentinel fill below would survive such a launch."""
+    from msda_b200 import _lib
+    from msda_b200 import functions as F
+    shapes = [(12, 19)]
+    g = make_inputs(shapes, N=2, M=16, D=16, Lq=None, P=4, dist="W", seed=61)
+    rnd = oracle.bf16_round if dtype == torch.bfloat16 else _fp16_round
+    g["value"] = rnd(g["value"]); g["grad_out"] = rnd(g["grad_out"])
+    args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
+    truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
+    tol = BF16_TOL if dtype == torch.bfloat16 else 2e-3
+    check_all(g, run_cuda(g, dtype, variant), truth, tol)
+    # and directly: every output element is written (poisoned buffer handed to the C ABI)
+    N, S, M, D, L, Lq, P = g["dims"]
+    value, sh, st, loc, attn = dev(g["value"], dtype), dev(g["shapes"]), dev(g["starts"]), dev(g["loc"]), dev(g["attn"])
+    out = torch.full((N, Lq, M * D), float("nan"), dtype=dtype, device="cuda")
+    code = _lib.MSDA_BF16 if dtype == torch.bfloat16 else _lib.MSDA_F16
+    rc = _lib.lib().msda_forward(value.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), attn.data_ptr(),
+                                 out.data_ptr(), N, S, M, D, L, Lq, P, code, variant, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    assert_close("output (poisoned buffer)", out.double().cpu().numpy(), truth[0], tol)
+
+
+def test_deterministic_mode_unnormalised_attention_weights():
+    """The op accepts any attention weights (the reference's gradcheck uses un-normalised ones); the fixed-point scale of
+    the deterministic mode must cover |attn| > 1 instead of wrapping its int64 accumulators."""
+    g = make_inputs(ENC_SMALL, N=1, M=8, D=32, Lq=None, P=4, dist="I", seed=13)
+    g["attn"] = (g["attn"] * 4096.0).astype(np.float32)
+    g["grad_out"] = (g["grad_out"] * 1e6).astype(np.float32)
+    args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
+    truth_gv = oracle.backward(*args, g["grad_out"], np.float64)[0]
+    gv = run_cuda(g, torch.float32, mode=1)[1]
+    assert_close("grad_value (deterministic, attn x 4096)", gv, truth_gv, FP32_TOL)

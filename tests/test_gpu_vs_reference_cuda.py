@@ -10,8 +10,15 @@ import torch
 from helpers import SWIN_T_800x1333, make_inputs
 from oracle import oracle, ref_cuda
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref/msda_ref_cuda.so not built")]
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _reference_build_present():
+    """The reference build is the strongest judge this suite has (grad_sampling_loc everywhere, index parity on integer
+    coordinates): its absence on a GPU box is a FAILURE, never a skip.  It is built by `python oracle/build_ref.py`
+    (or __graft_entry__.build()) where /root/reference is mounted and travels to the box in the snapshot."""
+    assert ref_cuda.available(), "oracle/_ref/msda_ref_cuda.so is missing -- run `python oracle/build_ref.py` before gpurun"
 
 
 def both(g, variant=0):
