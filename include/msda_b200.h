@@ -75,9 +75,15 @@ const char *msda_error_string(int code);
  * bit 9      : (backward, bf16)         MSDA_VARIANT_NO_NARROW -- leave the fp32 accumulator in the
  *             workspace and do not write grad_value; finish with msda_backward_finish_bf16()
  *             (bits 8/9 let a profiler bracket the scatter kernel alone; same kernels, same order)
+ * bit 10     : MSDA_VARIANT_OLD_TILED -- in query-tile order use the row-group vector kernels instead of the phase-
+ *             structured tile kernels (A/B measurements; both are complete implementations)
+ * bit 11     : MSDA_VARIANT_TILE_BWD -- (backward, query-tile order, D = 32, P = 4, L <= 4) use the tile backward (per-tile
+ *             counting sort by value row + row-stationary accumulation) instead of the default row-group kernel
  * other bits: reserved, must be 0. */
 #define MSDA_VARIANT_NO_ZERO 0x100
 #define MSDA_VARIANT_NO_NARROW 0x200
+#define MSDA_VARIANT_OLD_TILED 0x400
+#define MSDA_VARIANT_TILE_BWD 0x800
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output,
                  int batch, int spatial_size, int num_heads, int channels, int num_levels,

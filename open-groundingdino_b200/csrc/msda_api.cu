@@ -49,9 +49,9 @@ int pick_family(int variant, int dtype, int D, int P, int L, int Lq, int S, bool
 
 // The bf16 backward accumulates fp32 rows in the permuted channel order of acc_pos() whenever the head
 // width allows it; a function of (dtype, D) only, so every kernel family and the narrowing agree.
-// Exception: D = 32 with at least two levels uses the pair-cooperative whole-row reductions of msda_bwd.cu,
-// which write the natural channel order.
-bool acc_is_permuted(int dtype, int D, int L) { return is16(dtype) && D % 8 == 0 && !(D == 32 && L >= 2); }
+// Exception: D = 32 keeps the natural channel order -- its kernels (pair-cooperative whole-row reductions of msda_bwd.cu,
+// row-list flushes of msda_tile.cu) write whole 128-byte rows.
+bool acc_is_permuted(int dtype, int D, int L) { (void)L; return is16(dtype) && D % 8 == 0 && D != 32; }
 
 // variant bits 4..5: CTAs per SM the vector kernels are compiled for (1 -> 2, 2 -> 3, 3 -> 4); 0 picks the
 // measured best: 3 for the forward (gather-latency bound, profits from 24 resident warps), 2 for the
@@ -59,6 +59,21 @@ bool acc_is_permuted(int dtype, int D, int L) { return is16(dtype) && D % 8 == 0
 int min_blocks(int variant, int dflt) {
   const int sel = (variant >> 4) & 3;
   return sel == 0 ? dflt : sel + 1;
+}
+
+// query-tile order (family 3) runs on the tile kernels of msda_tile.cu where they exist; MSDA_VARIANT_OLD_TILED keeps the
+// round-1 vector kernels in that order (A/B measurements)
+bool use_tile_kernels(int variant, int family, int dtype, const Problem &pr) {
+  return family == 3 && !(variant & MSDA_VARIANT_OLD_TILED) && tile_supported(dtype, pr.N, pr.S, pr.M, pr.D, pr.L, pr.P);
+}
+
+int window_margin() {
+  static const int m = [] {
+    const char *e = getenv("MSDA_WIN_MARGIN");
+    const int v = e ? atoi(e) : 5;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+  }();
+  return m;
 }
 
 int vec_grid(const Problem &pr, int resident_per_sm) {
@@ -105,6 +120,7 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
   const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
   if (family == 1) return launch_forward_generic(pr, dtype, stream);
   pr.tiled = (family == 3);
+  if (use_tile_kernels(variant, family, dtype, pr)) return launch_forward_tile(pr, dtype, sm_count(), min_blocks(variant, 3), 0, stream);
   return launch_forward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 3)), min_blocks(variant, 3), stream);
 }
 
@@ -158,8 +174,14 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     rc = launch_backward_generic(pr, dtype, stream);
   } else {
     pr.tiled = (family == 3);
+    pr.win_margin = window_margin();
     const int abl = (variant >> 6) & 3;   // profiling ablations, see msda_bwd.cu
-    rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
+    // The tile backward (counting sort + row-stationary pass, msda_tile.cu) is correct and sends 3x fewer reductions to
+    // the L2, but measured slower than the row-group kernel (0.93 vs 0.75 ms at cfg-2, profiles/r02_tile_backward.md):
+    // opt-in through MSDA_VARIANT_TILE_BWD.
+    if ((variant & MSDA_VARIANT_TILE_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
+      rc = launch_backward_tile(pr, dtype, sm_count(), 0, stream);
+    else rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
   }
   if (rc != MSDA_OK) return rc;
   if (is16(dtype) && !(variant & MSDA_VARIANT_NO_NARROW))
@@ -195,7 +217,10 @@ int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const i
   pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
-  return launch_forward_vec(pr, dtype, vec_grid(pr, 3), (q_dtype == MSDA_BF16 ? 202 : q_dtype == MSDA_F16 ? 203 : 201), static_cast<cudaStream_t>(stream_));
+  const int pre = q_dtype == MSDA_BF16 ? 2 : q_dtype == MSDA_F16 ? 3 : 1;
+  if (use_tile_kernels(variant, pr.tiled ? 3 : 2, dtype, pr))
+    return launch_forward_tile(pr, dtype, sm_count(), 3, pre, static_cast<cudaStream_t>(stream_));
+  return launch_forward_vec(pr, dtype, vec_grid(pr, 3), 200 + pre, static_cast<cudaStream_t>(stream_));
 }
 
 int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -227,7 +252,9 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
     return MSDA_E_UNSUPPORTED;
   const size_t n_value = (size_t)N * S * M * D;
   if (cudaError_t e = cudaMemsetAsync(acc, 0, n_value * 4, stream)) return (int)e;
-  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), (q_dtype == MSDA_BF16 ? 202 : q_dtype == MSDA_F16 ? 203 : 201), stream);
+  const int pre = q_dtype == MSDA_BF16 ? 2 : q_dtype == MSDA_F16 ? 3 : 1;
+  pr.win_margin = window_margin();
+  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), 200 + pre, stream);
   if (rc != MSDA_OK) return rc;
   if (is16(dtype))
     rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0,

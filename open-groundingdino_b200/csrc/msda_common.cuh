@@ -44,6 +44,10 @@ struct Problem {
   // fused pre-op (msda_pre.cuh): loc/attn then hold raw offsets/logits, grad_loc/grad_attn their gradients
   const float *ref;        // reference points (N, Lq, L, ref_dim) fp32
   int ref_dim;             // 2 or 4
+  // value rows to treat as zero (MSDeformAttn's input_padding_mask, ops/modules/ms_deform_attn.py:95-96): (N, S) bytes,
+  // non-zero = padding; such rows gather as zero and receive no gradient.  nullptr = no mask.
+  const unsigned char *pad_mask;
+  int win_margin;          // tile kernels: halo (pixels) of the per-tile aggregation windows (msda_tile.cu)
 };
 
 // Position of channel c inside a head's fp32 accumulator row when the row is permuted (bf16 value,
@@ -118,6 +122,7 @@ struct UnitCtx {
   int b, m;              // tiled order: fixed per unit
   int y0, x0, Hq, Wq;    // tiled order: tile origin and the query level's extent
   int q0;                // tiled order: first query of that level
+  int lq;                // tiled order: that level
   int idx0;              // linear order: first item of the unit
 };
 
@@ -140,9 +145,10 @@ __device__ __forceinline__ UnitCtx decode_unit(const Problem &pr, const Tables &
     uc.Hq = tb.H[l];
     uc.Wq = tb.W[l];
     uc.q0 = tb.qstart[l];
+    uc.lq = l;
     uc.idx0 = 0;
   } else {
-    uc.b = uc.m = uc.y0 = uc.x0 = uc.Hq = uc.Wq = uc.q0 = 0;
+    uc.b = uc.m = uc.y0 = uc.x0 = uc.Hq = uc.Wq = uc.q0 = uc.lq = 0;
     uc.idx0 = unit * tb.unit_items;
   }
   return uc;

@@ -117,6 +117,19 @@ def test_cfg3_decoder_bs8(dtype, tol, small):
         _check(g, dtype, tol, small)
 
 
+@pytest.mark.parametrize("dist", ["I", "U"])
+def test_cfg2_tile_backward_bf16_bs4(dist):
+    """The opt-in tile backward (MSDA_VARIANT_TILE_BWD) at the headline size: every window level, directly handled samples
+    (U: nearly all of them) and the sort capacity limits are exercised only at full size."""
+    g = _round_inputs(make_inputs(SWIN_T_800x1333, N=4, M=8, D=32, Lq=None, P=4, dist=dist, seed=59), torch.bfloat16)
+    res = _ours(g, torch.bfloat16, variant=3 | 0x800)
+    theirs = _reference_op_wrapped(g, torch.bfloat16)
+    for name, got, want in zip(NAMES, res, theirs):
+        bound = 1e-2 if name in ("output", "grad_value") else 2e-5
+        err = oracle.normwise(got.reshape(want.shape), want)
+        assert err <= bound, f"{name} vs reference CUDA op: {err:.3e} > {bound:.1e}"
+
+
 def test_cfg1_fp32_bs1_every_family_vs_reference_op():
     """configs[0] shape on the GPU (fp32, bs 1), default dispatch, distribution I: all four results against the reference op."""
     g = make_inputs(SWIN_T_800x1333, N=1, M=8, D=32, Lq=None, P=4, dist="I", seed=53)

@@ -20,7 +20,10 @@ pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-5
 BF16_TOL = 1e-2
-FAMILIES = {"generic": 1, "vec_linear": 2, "vec_tiled": 3}
+# vec_tiled: query-tile order -- forward on the phase-structured tile kernel (csrc/msda_tile.cu) where it exists (D = 32,
+# P = 4, L <= 4), backward on the row-group vector kernel; rowgroup_tiled forces the row-group forward as well
+# (MSDA_VARIANT_OLD_TILED); tile_bwd opts into the tile backward (MSDA_VARIANT_TILE_BWD: counting sort + row-stationary pass)
+FAMILIES = {"generic": 1, "vec_linear": 2, "vec_tiled": 3, "rowgroup_tiled": 3 | 0x400, "tile_bwd": 3 | 0x800}
 
 
 def dev(a, dtype=None):
@@ -80,7 +83,7 @@ def test_reference_testpy_acceptance():
     assert np.allclose(out32, g["out_f32"], rtol=1e-2, atol=1e-3)
 
 
-@pytest.mark.parametrize("family", ["generic", "vec_linear"])
+@pytest.mark.parametrize("family", ["generic", "vec_linear", "vec_tiled", "rowgroup_tiled", "tile_bwd"])
 @pytest.mark.parametrize("name", ["pyr4_bf16_D32", "pyr4_wide_D32", "pyr5_P8_D16"])
 def test_golden_bf16_value(name, family):
     g = dict(load_golden(name))
@@ -110,7 +113,10 @@ def test_encoder_shaped_vs_oracle(dist, M, D, P):
         res = run_cuda(g, torch.float32, code)
         check_all(g, res, truth, FP32_TOL)
         outs[fam] = res[0]
-    assert np.array_equal(outs["vec_linear"], outs["vec_tiled"])
+    # the row-group kernels do the same per-item arithmetic in both orders: identical bits; the tile kernels sum the same
+    # 64 products in another order (per neighbour, then across neighbours)
+    assert np.array_equal(outs["vec_linear"], outs["rowgroup_tiled"])
+    assert oracle.normwise(outs["vec_tiled"], outs["vec_linear"]) <= 2e-6
 
 
 @pytest.mark.parametrize("L", [1, 2, 3, 5])
@@ -227,7 +233,7 @@ def _fp16_round(x):
     return torch.from_numpy(np.ascontiguousarray(x)).to(torch.float16).float().numpy()
 
 
-@pytest.mark.parametrize("family", ["generic", "vec_linear"])
+@pytest.mark.parametrize("family", ["generic", "vec_linear", "vec_tiled"])
 @pytest.mark.parametrize("name", ["pyr4_wide_D32", "pyr5_P8_D16", "testpy_D64"])
 def test_golden_fp16_value(name, family):
     """Native fp16 rows (the reference's --amp dtype): same contract as bf16 -- 16-bit value/grad, fp32 coordinates and
@@ -306,7 +312,7 @@ def test_window_aggregation_chains(kind, dtype):
         tol = BF16_TOL
     truth_out = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
     truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
-    for code in (2, 3):
+    for code in (2, 3, 3 | 0x400, 3 | 0x800):
         check_all(g, run_cuda(g, dtype, code), truth, tol)
 
 
