@@ -19,6 +19,14 @@ roofline     : the backward scatter kernel (dominant), bracketed by CUDA events 
 cpu_baseline : the reference's CPU path (grid_sample formulation, oracle/torch_port.py) on this host.
 --impl reference : that CPU path alone, same metric/unit/config, bounded sample per step.
 
+configs      : (N = 1) short runs of the other BASELINE.json configurations -- cfg-1 fp32 bs 1, cfg-3 decoder fp32 / bf16,
+               cfg-4 SwinB encoder / decoder shapes, cfg-2 on uniform random locations -- each with ms_per_step, the dominant
+               kernel's roofline fraction and the speed-up over the reference's own CUDA op on the same tensors.
+train        : BASELINE metric's second half -- training images/s of the reference's full model (SwinB, 1024 x 1024,
+               256 text tokens, bs 4 per GPU, bf16 autocast, DDP + NCCL) built by the reference's own builder with this
+               repo's attention dropped in (tools/train_step_bench.py, tools/refmodel.py); allreduce_bytes / nccl_ms from
+               a profiler trace of one step.
+
 N > 1 (torchrun): every rank runs the same per-GPU workload (the path shards by batch with no data-path
 collective -- "replicas only"); time = max over ranks, value = N x per-GPU bytes / time.
 """
@@ -217,6 +225,51 @@ class OurLayer:
         if self.code == L.MSDA_BF16:
             N, S, M_, D_, L_ = i["dims"][:5]
             L.check(self.lib.msda_backward_finish_bf16(self.ws.data_ptr(), self.gv.data_ptr(), N, S, M_, D_, L_, stream), "finish")
+
+
+def measure_config(torch, _lib, name, dist, variant, device, peak, steps=5, ref_steps=3):
+    """Short run of another configuration for the `configs` block (rank 0, N = 1)."""
+    cfg = CONFIGS[name]
+    layers = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, dist, 300 + l, device), variant) for l in range(cfg["layers"])]
+    nl = len(layers)
+
+    def step(events=None):
+        for lay in layers:
+            lay.forward()
+        for k, lay in enumerate(reversed(layers)):
+            lay.backward(*(events[k] if events else (None, None)))
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)] for _ in range(steps)]
+    e0, e1, f0, f1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    e0.record()
+    for k in range(steps):
+        step(ev[k])
+    e1.record()
+    f0.record()
+    for _ in range(3):
+        for lay in layers:
+            lay.forward()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    bwd_ms = sum(a.elapsed_time(b) for evs in ev for a, b in evs) / (steps * nl)
+    fwd_ms = f0.elapsed_time(f1) / (3 * nl)
+    N, S, _, _, L, Lq, _ = layers[0].i["dims"]
+    e_v = 2 if cfg["dtype"] == "bf16" else 4
+    b_fwd, b_bwd = algorithmic_bytes(N, S, L, Lq, e_v)
+    rec = {"workload": cfg["text"], "distribution": dist, "ms_per_step": ms_step, "layers": nl,
+           "value": (b_fwd + b_bwd) * nl / (ms_step * 1e-3) / 1e9, "unit": UNIT,
+           "step_frac": (b_fwd + b_bwd) * nl / (ms_step * 1e-3) / 1e9 / peak,
+           "roofline": {"kernel": "backward scatter kernel", "kernel_ms": bwd_ms, "achieved": b_bwd / (bwd_ms * 1e-3) / 1e9,
+                        "frac": b_bwd / (bwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": b_bwd,
+                        "fwd_kernel_ms": fwd_ms, "fwd_frac": b_fwd / (fwd_ms * 1e-3) / 1e9 / peak},
+           "reference_cuda_op": time_reference_cuda(torch, layers, cfg, ms_step, reps=ref_steps)}
+    del layers
+    torch.cuda.empty_cache()
+    return rec
 
 
 def cpu_reference_step(torch, cfg, threads, seed=1234):
@@ -421,6 +474,16 @@ def run_ours(args, cfg):
     if rank == 0 and not args.no_ref_cuda:
         extra["reference_cuda_op"] = time_reference_cuda(torch, layers, cfg, ms_step)
         extra["reference_grid_sample_cuda"] = time_grid_sample_cuda(torch, layers, cfg, ms_step)
+    if rank == 0 and world == 1 and not args.no_configs and args.config == "cfg2" and args.dist == "I":
+        block = {}
+        for key, (name, d) in {"cfg1_fp32_bs1": ("cfg1", "I"), "cfg3_decoder_fp32_bs8": ("cfg3", "I"),
+                               "cfg3_decoder_bf16_bs8": ("cfg3bf16", "I"), "cfg4_swinb_encoder_bf16_bs4": ("cfg4enc", "I"),
+                               "cfg4_swinb_decoder_bf16_bs4": ("cfg4dec", "I"), "cfg2_uniform_locations": ("cfg2", "U")}.items():
+            try:
+                block[key] = measure_config(torch, _lib, name, d, args.variant, device, peak)
+            except Exception as exc:     # pragma: no cover - e.g. out of memory on a shared box
+                block[key] = {"unavailable": repr(exc)[:160]}
+        extra["configs"] = block
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -435,6 +498,16 @@ def run_ours(args, cfg):
         cpu = {"value": sample_bytes(cfg) / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": desc + f"; {reps} reps, {dt * 1e3:.0f} ms each", "ms_per_sample": dt * 1e3}
 
+    train = None
+    if not args.no_train:
+        del layers
+        torch.cuda.empty_cache()
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import train_step_bench
+            train = train_step_bench.run(msda="ours", sync_free=True, steps=args.train_steps, warmup=2, device=device, init_dist=False)
+        except Exception as exc:         # the reference copy (baseline/_ref/src) is missing, out of memory, ...
+            train = {"unavailable": repr(exc)[:200]}
     if rank == 0:
         launches_per_step = nl * (1 + 1 + (1 if code == _lib.MSDA_BF16 else 0))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -447,14 +520,15 @@ def run_ours(args, cfg):
                            "l2_policy": "inputs larger than L2 (each layer has its own %.0f MB of tensors)" % (step_bytes / nl / 1e6),
                            "algorithmic_bytes_per_step": step_bytes},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "clocks": clocks.summary(), "ms_fwd_per_layer": fwd_kernel_ms, "ms_bwd_kernel_per_layer": bwd_kernel_ms}
+                "clocks": clocks.summary(), "ms_fwd_per_layer": fwd_kernel_ms, "ms_bwd_kernel_per_layer": bwd_kernel_ms,
+                "train": train}
         line.update(extra)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def time_reference_cuda(torch, layers, cfg, ours_ms_step):
+def time_reference_cuda(torch, layers, cfg, ours_ms_step, reps=5):
     """The reference's own CUDA op (oracle/_ref, fp32 only) on the same tensors, same step structure.  For a
     bf16 workload it is wrapped exactly like the reference wraps fp16 (ops/modules/ms_deform_attn.py:114-120):
     widen value/grad to fp32, run, narrow the result; the casts are inside its time."""
@@ -486,7 +560,6 @@ def time_reference_cuda(torch, layers, cfg, ours_ms_step):
         step()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
     a.record()
     for _ in range(reps):
         step()
@@ -739,6 +812,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configurations (N = 1)")
+    ap.add_argument("--no-train", action="store_true", help="skip the full-model training-step record")
+    ap.add_argument("--train-steps", type=int, default=5)
     ap.add_argument("--workload", default="msda", choices=["msda", "matcher"],
                     help="msda = the BASELINE.json metric (default); matcher = scope row f2 (single GPU)")
     args = ap.parse_args()

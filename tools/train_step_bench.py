@@ -72,7 +72,13 @@ def run(msda="ours", sync_free=True, steps=5, warmup=2, batch=4, size=1024, back
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], find_unused_parameters=False)
+        # main.py:259-260: DistributedDataParallel(model, device_ids=[gpu], find_unused_parameters=...) + _set_static_graph().
+        # The step is host-bound (the host needs ~345 ms to issue it), so DDP's own host work shows 1:1: with its defaults
+        # (25 MB buckets, gradients copied into the buckets) a step took 373 ms on 2 GPUs against 346 ms on 1; with one
+        # 512 MB bucket size and gradients as bucket views 354.5 ms (profiles/r02_train_step.md).  Results are unaffected.
+        ddp_kw = {"bucket_cap_mb": int(os.environ.get("MSDA_DDP_BUCKET_MB", "512")),
+                  "gradient_as_bucket_view": os.environ.get("MSDA_DDP_BUCKET_VIEW", "1") == "1"}
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], find_unused_parameters=False, **ddp_kw)
         net._set_static_graph()
     step = refmodel.TrainStep(net, criterion, args, amp_dtype=torch.bfloat16)
     images, targets, cats, caps = refmodel.make_batch(batch, size, size, device, max_text_len=text_len, seed=100 + rank)
@@ -124,7 +130,7 @@ def run(msda="ours", sync_free=True, steps=5, warmup=2, batch=4, size=1024, back
            "steps": steps, "warmup": warmup, "loss_last": float(loss), "params_total": n_params, "params_trainable": n_train,
            "allreduce_bytes": n_train * 4 if world > 1 else 0, "nccl_ms": nccl_ms, "own_kernels_ms": msda_ms,
            "model": f"reference build_groundingdino, {backbone}, {size}x{size}, {text_len} text tokens, bf16 autocast, "
-                    f"checkpointing on, AdamW, DDP static graph", "msda": msda, "sync_free_patch": bool(sync_free),
+                    f"checkpointing on, AdamW, DDP static graph (bucket_cap_mb 512, gradient_as_bucket_view)", "msda": msda, "sync_free_patch": bool(sync_free),
            "peak_mem_gb": torch.cuda.max_memory_allocated(device) / 1e9}
     return rec
 
