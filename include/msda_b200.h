@@ -131,6 +131,23 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
                         int num_point, int ref_dim, int value_dtype, int q_dtype, int variant, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* The same with MSDeformAttn's input_padding_mask folded in (scope row f4, ops/modules/ms_deform_attn.py:95-96):
+ * padding_mask is (N, S) bytes, non-zero = padding (a torch.bool tensor as is), or NULL.  Value rows flagged as padding
+ * gather as zero and their grad_value rows are zero -- exactly what `value.masked_fill(mask[..., None], 0)` and its
+ * backward give -- so the caller feeds the value_proj output directly and the masked_fill pass over the whole value
+ * tensor (and its backward) disappears. */
+int msda_fused_forward_masked(const void *value, const unsigned char *padding_mask, const int64_t *spatial_shapes,
+                              const int64_t *level_start_index, const void *sampling_offsets, const void *attn_logits,
+                              const float *reference_points, void *output, int batch, int spatial_size, int num_heads,
+                              int channels, int num_levels, int num_query, int num_point, int ref_dim, int value_dtype,
+                              int q_dtype, int variant, void *stream);
+int msda_fused_backward_masked(const void *value, const unsigned char *padding_mask, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, const void *sampling_offsets, const void *attn_logits,
+                               const float *reference_points, const void *grad_output, void *grad_value, void *grad_offsets,
+                               void *grad_logits, int batch, int spatial_size, int num_heads, int channels, int num_levels,
+                               int num_query, int num_point, int ref_dim, int value_dtype, int q_dtype, int variant,
+                               void *workspace, size_t workspace_bytes, void *stream);
+
 /* rec: int32 (N, Lq, M, L, P, 4) = [h_low, w_low, flags, slab_row]; flags bit0 = sample accepted,
  * bits1..4 = which of the 4 neighbours exist; slab_row = b*S + level_start_index[l].  fp32 path. */
 int msda_sample_index(const int64_t *spatial_shapes, const int64_t *level_start_index,

@@ -203,6 +203,14 @@ int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const i
                        const void *sampling_offsets, const void *attn_logits, const float *reference_points,
                        void *output, int N, int S, int M, int D, int L, int Lq, int P, int ref_dim, int dtype,
                        int q_dtype, int variant, void *stream_) {
+  return msda_fused_forward_masked(value, nullptr, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                   reference_points, output, N, S, M, D, L, Lq, P, ref_dim, dtype, q_dtype, variant, stream_);
+}
+
+int msda_fused_forward_masked(const void *value, const unsigned char *padding_mask, const int64_t *spatial_shapes,
+                              const int64_t *level_start_index, const void *sampling_offsets, const void *attn_logits,
+                              const float *reference_points, void *output, int N, int S, int M, int D, int L, int Lq, int P,
+                              int ref_dim, int dtype, int q_dtype, int variant, void *stream_) {
   if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points || !output)
     return MSDA_E_INVALID;
   if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
@@ -215,6 +223,7 @@ int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const i
   pr.value = value; pr.shapes = spatial_shapes; pr.starts = level_start_index;
   pr.loc = sampling_offsets; pr.attn = attn_logits; pr.ref = reference_points; pr.ref_dim = ref_dim; pr.out = output;
   pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.pad_mask = padding_mask;
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
   const int pre = q_dtype == MSDA_BF16 ? 2 : q_dtype == MSDA_F16 ? 3 : 1;
@@ -228,6 +237,16 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
                         const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits, int N, int S,
                         int M, int D, int L, int Lq, int P, int ref_dim, int dtype, int q_dtype, int variant,
                         void *workspace, size_t workspace_bytes, void *stream_) {
+  return msda_fused_backward_masked(value, nullptr, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                    reference_points, grad_output, grad_value, grad_offsets, grad_logits, N, S, M, D, L, Lq, P,
+                                    ref_dim, dtype, q_dtype, variant, workspace, workspace_bytes, stream_);
+}
+
+int msda_fused_backward_masked(const void *value, const unsigned char *padding_mask, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, const void *sampling_offsets, const void *attn_logits,
+                               const float *reference_points, const void *grad_output, void *grad_value, void *grad_offsets,
+                               void *grad_logits, int N, int S, int M, int D, int L, int Lq, int P, int ref_dim, int dtype,
+                               int q_dtype, int variant, void *workspace, size_t workspace_bytes, void *stream_) {
   if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
       !grad_output || !grad_value || !grad_offsets || !grad_logits)
     return MSDA_E_INVALID;
@@ -242,6 +261,7 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
   pr.loc = sampling_offsets; pr.attn = attn_logits; pr.ref = reference_points; pr.ref_dim = ref_dim;
   pr.grad_out = grad_output; pr.grad_loc = grad_offsets; pr.grad_attn = grad_logits;
   pr.N = N; pr.S = S; pr.M = M; pr.D = D; pr.L = L; pr.Lq = Lq; pr.P = P;
+  pr.pad_mask = padding_mask;
   pr.tile_w_log2 = 3;
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
   void *acc = is16(dtype) ? workspace : grad_value;

@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         for (int p = 0; p < P; ++p) {
           const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
           const bool in = act && c.inside;
-          const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+          int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+          if (pr.pad_mask != nullptr && mask != 0)
+            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
           g_lh[p] = in ? c.lh : 0.f;
           g_lw[p] = in ? c.lw : 0.f;
           g_aw[p] = in ? a[p] : 0.f;

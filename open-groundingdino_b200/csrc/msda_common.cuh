@@ -244,6 +244,18 @@ __device__ __forceinline__ int corner_mask(int h_low, int w_low, int H, int W) {
          ((int)(bottom && right) << 3);
 }
 
+// input_padding_mask inside the kernels (scope row f4): neighbours whose value row is padding are treated like neighbours
+// outside the image -- they gather as zero and receive no gradient, which is what MSDeformAttn's
+// value.masked_fill(mask, 0) (ops/modules/ms_deform_attn.py:95-96) and its backward do.  `row00` = b*S + level start +
+// h_low*W + w_low.
+__device__ __forceinline__ int drop_padded(const unsigned char *__restrict__ pad, int mask, int row00, int W) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    if ((mask >> kk) & 1)
+      if (__ldg(pad + row00 + (kk & 1) + ((kk & 2) ? W : 0)) != 0) mask &= ~(1 << kk);
+  return mask;
+}
+
 // Packed fp32x2 math (sm_100+: one FFMA2 issue slot for two lanes of the accumulator).
 __device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
   unsigned long long r;

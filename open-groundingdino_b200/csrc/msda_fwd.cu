@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
             const int p = p0 + pp;
             const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
             const bool in = act && c.inside;
-            const int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+            int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+            if (pr.pad_mask != nullptr && mask != 0)
+              mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
             const float aw = in ? a[p] : 0.f;
             const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
             const float hh = 1.f - lh, hw = 1.f - lw;

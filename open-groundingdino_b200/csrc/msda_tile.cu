@@ -173,12 +173,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
         const float ah = hh * s.aw, al = s.lh * s.aw;
         const float cw[4] = {ah * hw, ah * s.lw, al * hw, al * s.lw};
         int mask = s.mask;
-        if (pr.pad_mask != nullptr) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            if ((mask >> kk) & 1)
-              if (__ldg(pr.pad_mask + s.r00 + (kk & 1) + ((kk & 2) ? W : 0)) != 0) mask &= ~(1 << kk);
-        }
+        if (pr.pad_mask != nullptr && mask != 0) mask = drop_padded(pr.pad_mask, mask, s.r00, W);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int r = s.r00 + (kk & 1) + ((kk & 2) ? W : 0);
@@ -395,12 +390,7 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr)
       const float ah = hh * s.aw, al = s.lh * s.aw;
       const float cw[4] = {ah * hw, ah * s.lw, al * hw, al * s.lw};
       int mask = s.mask;
-      if (pr.pad_mask != nullptr) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          if ((mask >> kk) & 1)
-            if (__ldg(pr.pad_mask + s.r00 + (kk & 1) + ((kk & 2) ? W : 0)) != 0) mask &= ~(1 << kk);
-      }
+      if (pr.pad_mask != nullptr && mask != 0) mask = drop_padded(pr.pad_mask, mask, s.r00, W);
       // the cell's existing rows / columns must lie inside the window
       const int wr = s.h_low - win.y0, wc = s.w_low - win.x0;
       const int r_lo = wr + ((mask & 3) ? 0 : 1), r_hi = wr + ((mask & 12) ? 1 : 0);

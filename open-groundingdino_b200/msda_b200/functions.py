@@ -189,14 +189,28 @@ def _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, atte
     return N, S, M, D, L, Lq, P
 
 
-def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
-    """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D)."""
+def _mask_ptr(padding_mask, N, S):
+    """input_padding_mask (N, S) bool / uint8, True = padding (ops/modules/ms_deform_attn.py:95-96) -> byte pointer or None."""
+    if padding_mask is None:
+        return None, None
+    _require(padding_mask.is_cuda and tuple(padding_mask.shape) == (N, S), "padding mask must be a CUDA tensor of shape (N, S)")
+    _require(padding_mask.dtype in (torch.bool, torch.uint8), "padding mask must be bool or uint8")
+    m = padding_mask.contiguous()
+    m = m.view(torch.uint8) if m.dtype == torch.bool else m
+    return m, m.data_ptr()
+
+
+def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
+                  padding_mask=None):
+    """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D).
+    With ``padding_mask`` the rows it flags gather as zero (no masked_fill pass over ``value`` needed)."""
     N, S, M, D, L, Lq, P = _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits,
                                        reference_points)
+    mask_keep, mask_ptr = _mask_ptr(padding_mask, N, S)
     with torch.cuda.device(value.device):
         output = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
-        rc = _lib.lib().msda_fused_forward(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+        rc = _lib.lib().msda_fused_forward_masked(
+            value.data_ptr(), mask_ptr, spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
             attention_logits.data_ptr(), reference_points.data_ptr(), output.data_ptr(), N, S, M, D, L, Lq, P,
             reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], 0,
             torch.cuda.current_stream().cuda_stream)
@@ -205,13 +219,14 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
 
 
 def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
-                   grad_output):
-    """-> (grad_value, grad_sampling_offsets, grad_attention_logits)"""
+                   grad_output, padding_mask=None):
+    """-> (grad_value, grad_sampling_offsets, grad_attention_logits); grad_value rows flagged by ``padding_mask`` are zero."""
     grad_output = grad_output.contiguous().to(value.dtype)
     N, S, M, D, L, Lq, P = _fused_dims(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits,
                                        reference_points)
     _check_inputs((("grad_output", grad_output),))
     _require(grad_output.numel() == N * Lq * M * D, "grad_output must be (N, Lq, M*D)")
+    mask_keep, mask_ptr = _mask_ptr(padding_mask, N, S)
     code = _DTYPE_CODE[value.dtype]
     with torch.cuda.device(value.device):
         grad_value = torch.empty_like(value)
@@ -219,8 +234,8 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
         grad_logits = torch.empty_like(attention_logits)
         ws_bytes = _lib.lib().msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, _lib.MSDA_BWD_ATOMIC)
         workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
-        rc = _lib.lib().msda_fused_backward(
-            value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
+        rc = _lib.lib().msda_fused_backward_masked(
+            value.data_ptr(), mask_ptr, spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
             attention_logits.data_ptr(), reference_points.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
             grad_offsets.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, reference_points.shape[-1], code,
             _DTYPE_CODE[sampling_offsets.dtype], 0, workspace.data_ptr() if workspace is not None else None, ws_bytes,
@@ -232,13 +247,16 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
 class MSDeformAttnFusedFunction(Function):
     """softmax + sampling-location arithmetic + multi-scale deformable attention in one kernel each way.
     forward(value (N,S,M,D), spatial_shapes, level_start_index, sampling_offsets (N,Lq,M,L,P,2),
-            attention_logits (N,Lq,M,L*P), reference_points (N,Lq,L,2|4)) -> (N, Lq, M*D)"""
+            attention_logits (N,Lq,M,L*P), reference_points (N,Lq,L,2|4), padding_mask (N,S) bool or None) -> (N, Lq, M*D)"""
 
     @staticmethod
-    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points):
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
+                padding_mask=None):
         reference_points = reference_points.detach().to(torch.float32).contiguous()
-        output = fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points)
+        output = fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
+                               padding_mask)
         ctx.save_for_backward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points)
+        ctx.padding_mask = padding_mask
         return output
 
     @staticmethod
@@ -246,5 +264,5 @@ class MSDeformAttnFusedFunction(Function):
     def backward(ctx, grad_output):
         value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points = ctx.saved_tensors
         grad_value, grad_offsets, grad_logits = fused_backward(value, spatial_shapes, level_start_index, sampling_offsets,
-                                                               attention_logits, reference_points, grad_output)
-        return grad_value, None, None, grad_offsets, grad_logits, None
+                                                               attention_logits, reference_points, grad_output, ctx.padding_mask)
+        return grad_value, None, None, grad_offsets, grad_logits, None, None

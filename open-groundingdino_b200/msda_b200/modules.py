@@ -54,6 +54,9 @@ class MSDeformAttn(nn.Module):
     #: fp16 values (the reference's --amp mode) run on native fp16-row kernels instead of being widened to fp32 around
     #: the op; False restores the reference's branch (:114-120) literally.
     native_fp16 = True
+    #: hand input_padding_mask to the fused kernels (padded rows gather as zero, zero grad_value rows) instead of running
+    #: value.masked_fill over the whole value tensor (scope row f4); False = the reference's masked_fill (:95-96)
+    mask_in_kernel = True
     #: call the kernels through torch.ops.msda_b200.* (msda_b200/torch_ops.py) so that selective activation
     #: checkpointing can keep the op's output instead of recomputing it
     use_dispatcher_ops = False
@@ -104,23 +107,28 @@ class MSDeformAttn(nn.Module):
         if self.validate_shapes:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        value = self.value_proj(input_flatten).view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         if (self.fuse_pre_op and (value.dtype != torch.float16 or self.native_fp16)
                 and value.is_contiguous() and offsets.is_contiguous() and weights.is_contiguous()
                 and fused_supported(value, offsets, weights, reference_points, self.n_levels, self.n_points)):
+            mask = None
+            if input_padding_mask is not None:
+                if self.mask_in_kernel:
+                    mask = input_padding_mask                        # folded into the gather / scatter
+                else:
+                    value = value.masked_fill(input_padding_mask[..., None, None], float(0))
             if self.use_dispatcher_ops:
                 from . import torch_ops  # noqa: F401  (registers torch.ops.msda_b200)
                 out = torch.ops.msda_b200.fused_forward(value, input_spatial_shapes, input_level_start_index, offsets,
-                                                        weights, reference_points.detach().float().contiguous())
+                                                        weights, reference_points.detach().float().contiguous(), mask)
             else:
                 out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index, offsets,
-                                                      weights, reference_points)
+                                                      weights, reference_points, mask)
             return self.output_proj(out)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None, None], float(0))
         weights = F.softmax(weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         locations = sampling_locations_from(reference_points, offsets, input_spatial_shapes, self.n_points)
 

@@ -26,9 +26,9 @@ _lib_def.define("forward(Tensor value, Tensor spatial_shapes, Tensor level_start
 _lib_def.define("backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, Tensor sampling_loc, "
                 "Tensor attn_weight, Tensor grad_output, int im2col_step) -> (Tensor, Tensor, Tensor)")
 _lib_def.define("fused_forward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, Tensor sampling_offsets, "
-                "Tensor attn_logits, Tensor reference_points) -> Tensor")
+                "Tensor attn_logits, Tensor reference_points, Tensor? padding_mask=None) -> Tensor")
 _lib_def.define("fused_backward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, Tensor sampling_offsets, "
-                "Tensor attn_logits, Tensor reference_points, Tensor grad_output) -> (Tensor, Tensor, Tensor)")
+                "Tensor attn_logits, Tensor reference_points, Tensor grad_output, Tensor? padding_mask=None) -> (Tensor, Tensor, Tensor)")
 
 
 @torch.library.impl(_lib_def, "forward", "CUDA")
@@ -44,14 +44,15 @@ def _backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weigh
 
 
 @torch.library.impl(_lib_def, "fused_forward", "CUDA")
-def _fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
-    return F.fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)
+def _fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, padding_mask=None):
+    return F.fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, padding_mask)
 
 
 @torch.library.impl(_lib_def, "fused_backward", "CUDA")
-def _fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output):
+def _fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output,
+                    padding_mask=None):
     return F.fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                            grad_output)
+                            grad_output, padding_mask)
 
 
 @torch.library.register_fake("msda_b200::forward")
@@ -65,12 +66,13 @@ def _backward_fake(value, spatial_shapes, level_start_index, sampling_loc, attn_
 
 
 @torch.library.register_fake("msda_b200::fused_forward")
-def _fused_forward_fake(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
+def _fused_forward_fake(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, padding_mask=None):
     return value.new_empty((value.shape[0], sampling_offsets.shape[1], value.shape[2] * value.shape[3]))
 
 
 @torch.library.register_fake("msda_b200::fused_backward")
-def _fused_backward_fake(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output):
+def _fused_backward_fake(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output,
+                         padding_mask=None):
     return torch.empty_like(value), torch.empty_like(sampling_offsets), torch.empty_like(attn_logits)
 
 
@@ -88,14 +90,15 @@ def _bwd(ctx, grad_output):
 
 
 def _fused_setup(ctx, inputs, output):
-    ctx.save_for_backward(*inputs)
+    ctx.save_for_backward(*inputs[:6])
+    ctx.padding_mask = inputs[6] if len(inputs) > 6 else None
 
 
 def _fused_bwd(ctx, grad_output):
     value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points = ctx.saved_tensors
     gv, go, gg = torch.ops.msda_b200.fused_backward(value, spatial_shapes, level_start_index, sampling_offsets,
-                                                    attn_logits, reference_points, grad_output.contiguous())
-    return gv, None, None, go, gg, None
+                                                    attn_logits, reference_points, grad_output.contiguous(), ctx.padding_mask)
+    return gv, None, None, go, gg, None, None
 
 
 torch.library.register_autograd("msda_b200::forward", _bwd, setup_context=_setup)
