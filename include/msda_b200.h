@@ -69,7 +69,8 @@ const char *msda_error_string(int code);
 /* Variant selector for experiments and A/B profiling; 0 = the library's default choice.
  * bit 0..3  : kernel family (1 = generic per-channel kernels, 2 = vector kernels, linear order,
  *             3 = vector kernels, query-tile order)
- * bit 4..5  : CTAs/SM the vector kernels are register-limited for (0: default, 1: 2, 2: 3, 3: 4)
+ * bit 4..5  : CTAs/SM the vector kernels are register-limited for (0: default, 1: 2, 2: 3, 3: 4); non-default values need a
+ *             library built with -DMSDA_BUILD_VARIANTS (MSDA_NVCC_EXTRA), otherwise MSDA_E_UNSUPPORTED
  * bit 8      : (backward, atomic mode) MSDA_VARIANT_NO_ZERO   -- the caller has already zeroed the
  *             accumulator (grad_value, or the workspace for bf16); skip the memset
  * bit 9      : (backward, bf16)         MSDA_VARIANT_NO_NARROW -- leave the fp32 accumulator in the
@@ -136,6 +137,8 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
  * gather as zero and their grad_value rows are zero -- exactly what `value.masked_fill(mask[..., None], 0)` and its
  * backward give -- so the caller feeds the value_proj output directly and the masked_fill pass over the whole value
  * tensor (and its backward) disappears. */
+/* whether the masked entry points accept a non-NULL mask for this geometry (the model's own: 8 heads, 4 levels) */
+int msda_fused_mask_supported(int num_heads, int num_levels);
 int msda_fused_forward_masked(const void *value, const unsigned char *padding_mask, const int64_t *spatial_shapes,
                               const int64_t *level_start_index, const void *sampling_offsets, const void *attn_logits,
                               const float *reference_points, void *output, int batch, int spatial_size, int num_heads,

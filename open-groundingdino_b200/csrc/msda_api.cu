@@ -199,6 +199,8 @@ int msda_fused_supported(int D, int L, int P, int value_dtype, int q_dtype) {
   return 0;
 }
 
+int msda_fused_mask_supported(int M, int L) { return (M == 8 && L == 4) ? 1 : 0; }
+
 int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                        const void *sampling_offsets, const void *attn_logits, const float *reference_points,
                        void *output, int N, int S, int M, int D, int L, int Lq, int P, int ref_dim, int dtype,
@@ -216,6 +218,7 @@ int msda_fused_forward_masked(const void *value, const unsigned char *padding_ma
   if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
   if (ref_dim != 2 && ref_dim != 4) return MSDA_E_INVALID;
   if (!msda_fused_supported(D, L, P, dtype, q_dtype)) return MSDA_E_UNSUPPORTED;
+  if (padding_mask && !msda_fused_mask_supported(M, L)) return MSDA_E_UNSUPPORTED;
   if (!(aligned16(value) && aligned16(sampling_offsets) && aligned16(attn_logits) && aligned16(reference_points) &&
         aligned16(output)))
     return MSDA_E_UNSUPPORTED;
@@ -253,6 +256,7 @@ int msda_fused_backward_masked(const void *value, const unsigned char *padding_m
   if (int rc = check_dims(N, S, M, D, L, Lq, P, dtype)) return rc;
   if (ref_dim != 2 && ref_dim != 4) return MSDA_E_INVALID;
   if (!msda_fused_supported(D, L, P, dtype, q_dtype)) return MSDA_E_UNSUPPORTED;
+  if (padding_mask && !msda_fused_mask_supported(M, L)) return MSDA_E_UNSUPPORTED;
   const size_t need = msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, dtype, MSDA_BWD_ATOMIC);
   if (need > 0 && (!workspace || workspace_bytes < need)) return MSDA_E_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

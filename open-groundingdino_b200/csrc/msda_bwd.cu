@@ -177,8 +177,10 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
           const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
           const bool in = act && c.inside;
           int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          if (pr.pad_mask != nullptr && mask != 0)
-            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          if constexpr (SPEC) {       // see msda_fwd.cu
+            if (pr.pad_mask != nullptr && mask != 0)
+              mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          }
           g_lh[p] = in ? c.lh : 0.f;
           g_lw[p] = in ? c.lw : 0.f;
           g_aw[p] = in ? a[p] : 0.f;
@@ -384,8 +386,10 @@ static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
     }
     MSDA_FUSED(201, 1) MSDA_FUSED(202, 2) MSDA_FUSED(203, 3)
 #undef MSDA_FUSED
-    if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }   // ablations
+#ifdef MSDA_BUILD_VARIANTS      // profiling ablations (variant bits 6..7)
+    if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
     if (minb == 102) { bwd_vec_kernel<VT, D, P, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+#endif
   }
   if (minb >= 100) return MSDA_E_UNSUPPORTED;
   if constexpr (D == 32 && P == 4) {
@@ -394,9 +398,12 @@ static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
       return (int)cudaGetLastError();
     }
   }
-  if (minb == 4) bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr);
-  else if (minb == 3) bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr);
-  else bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+#ifdef MSDA_BUILD_VARIANTS      // occupancy experiments (variant bits 4..5): 3 and 4 CTAs per SM spill and lose (tools/sweep.py)
+  if (minb == 4) { bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+  if (minb == 3) { bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+#endif
+  if (minb != 2) return MSDA_E_UNSUPPORTED;
+  bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
   return (int)cudaGetLastError();
 }
 

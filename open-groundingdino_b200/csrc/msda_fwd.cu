@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
             const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
             const bool in = act && c.inside;
             int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-            if (pr.pad_mask != nullptr && mask != 0)
-              mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+            if constexpr (SPEC) {     // the model's own geometry only: in the generic instantiations the extra live values spill
+              if (pr.pad_mask != nullptr && mask != 0)
+                mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+            }
             const float aw = in ? a[p] : 0.f;
             const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
             const float hh = 1.f - lh, hw = 1.f - lw;
@@ -211,9 +213,14 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
       return (int)cudaGetLastError();
     }
   }
-  if (minb == 4) fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr);
-  else if (minb == 3) fwd_vec_kernel<VT, D, P, 3, PB3><<<grid, kThreads, 0, stream>>>(pr);
-  else fwd_vec_kernel<VT, D, P, 2, PB2><<<grid, kThreads, 0, stream>>>(pr);
+#ifdef MSDA_BUILD_VARIANTS      // occupancy experiments (variant bits 4..5); the product build carries the measured best only
+  if (minb == 4) { fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+  if (minb == 2) { fwd_vec_kernel<VT, D, P, 2, PB2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+#else
+  (void)PB2;
+#endif
+  if (minb != 3) return MSDA_E_UNSUPPORTED;
+  fwd_vec_kernel<VT, D, P, 3, PB3><<<grid, kThreads, 0, stream>>>(pr);
   return (int)cudaGetLastError();
 }
 

@@ -681,7 +681,9 @@ int launch_fwd(const Problem &pr, int sms, int minb, int pre, cudaStream_t strea
     return (int)cudaGetLastError();                                                  \
   }
   MSDA_TILE_FWD(0, 3) MSDA_TILE_FWD(1, 3) MSDA_TILE_FWD(2, 3) MSDA_TILE_FWD(3, 3)
+#ifdef MSDA_BUILD_VARIANTS
   MSDA_TILE_FWD(0, 2)
+#endif
 #undef MSDA_TILE_FWD
   return MSDA_E_UNSUPPORTED;
 }
@@ -710,7 +712,11 @@ bool tile_supported(int dtype, int N, int S, int M, int D, int L, int P) {
 // pre: 0 = sampling locations / attention weights given; 1 / 2 / 3 = raw fp32 / bf16 / fp16 offsets and logits (msda_pre.cuh)
 // minb: resident CTAs per SM the kernel is compiled for (3 = default; 2 exists for the op boundary, A/B)
 int launch_forward_tile(const Problem &pr, int dtype, int sms, int minb, int pre, cudaStream_t stream) {
+#ifdef MSDA_BUILD_VARIANTS
   if (pre != 0 || minb != 2) minb = 3;
+#else
+  minb = 3;
+#endif
   if (dtype == MSDA_F32) return launch_fwd<wide_f32>(pr, sms, minb, pre, stream);
   if (dtype == MSDA_BF16) return launch_fwd<__nv_bfloat16>(pr, sms, minb, pre, stream);
   if (dtype == MSDA_F16) return launch_fwd<__half>(pr, sms, minb, pre, stream);

@@ -20,7 +20,7 @@ VARIANT_NO_ZERO, VARIANT_NO_NARROW = 0x100, 0x200
 EXPORTS = (
     "msda_abi_version", "msda_error_string", "msda_forward", "msda_backward_workspace_bytes", "msda_backward",
     "msda_backward_finish_bf16", "msda_fused_supported", "msda_fused_forward", "msda_fused_backward",
-    "msda_fused_forward_masked", "msda_fused_backward_masked",
+    "msda_fused_mask_supported", "msda_fused_forward_masked", "msda_fused_backward_masked",
     "msda_sample_index", "msda_host_create", "msda_host_destroy", "msda_host_h2d_bytes", "msda_host_d2h_bytes",
     "msda_host_fwd_bwd", "msda_host_submit", "msda_host_wait",
 )
@@ -53,6 +53,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.msda_fused_forward.argtypes = [vp] * 7 + [i] * 7 + [i, i, i, i, vp]
     lib.msda_fused_backward.restype = i
     lib.msda_fused_backward.argtypes = [vp] * 10 + [i] * 7 + [i, i, i, i, vp, sz, vp]
+    lib.msda_fused_mask_supported.restype = i
+    lib.msda_fused_mask_supported.argtypes = [i, i]
     lib.msda_fused_forward_masked.restype = i
     lib.msda_fused_forward_masked.argtypes = [vp] * 8 + [i] * 7 + [i, i, i, i, vp]
     lib.msda_fused_backward_masked.restype = i

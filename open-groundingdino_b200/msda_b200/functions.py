@@ -200,6 +200,11 @@ def _mask_ptr(padding_mask, N, S):
     return m, m.data_ptr()
 
 
+def fused_mask_supported(n_heads: int, n_levels: int) -> bool:
+    """True when the fused kernels can take input_padding_mask themselves for this geometry."""
+    return bool(_lib.lib().msda_fused_mask_supported(n_heads, n_levels))
+
+
 def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, reference_points,
                   padding_mask=None):
     """(N,S,M,D), tables, raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P), reference points fp32 -> (N, Lq, M*D).

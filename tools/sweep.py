@@ -37,7 +37,7 @@ def time_case(cfg_name, dist, variant, iters=10, nl=3):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--cases", default="cfg2:I:0,cfg2:I:2,cfg2:U:0,cfg2:U:2,cfg1:I:0,cfg1:U:0,cfg3:I:0,cfg2:I:0x10,cfg2:I:0x20")
+    ap.add_argument("--cases", default="cfg2:I:0,cfg2:I:0x400,cfg2:I:0x800,cfg2:U:0,cfg2:U:0x800,cfg1:I:0,cfg1:U:0,cfg3:I:0,cfg4enc:I:0")
     ap.add_argument("--iters", type=int, default=10)
     a = ap.parse_args()
     for c in a.cases.split(","):
