@@ -345,7 +345,10 @@ def run_ours(args, cfg):
     def max_over_ranks(x):
         return dist_utils.max_over_ranks(x, device)
 
-    layers = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, args.dist, 100 + l, device), args.variant)
+    # the job's global batch is partitioned over the ranks by image (no data-path collective: DESIGN.md section 7)
+    lo, hi = dist_utils.shard_bounds(world * cfg["N"], world, rank)
+    cfg = dict(cfg, N=hi - lo)
+    layers = [OurLayer(torch, _lib, make_layer_inputs(torch, cfg, args.dist, 100 + l + 1000 * rank, device), args.variant)
               for l in range(cfg["layers"])]
     nl = len(layers)
 
@@ -370,7 +373,8 @@ def run_ours(args, cfg):
             step(bwd_events[k])
         e1.record()
         barrier()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ms_step_local = e0.elapsed_time(e1) / args.steps
+    ms_step = max_over_ranks(ms_step_local)
     bwd_kernel_ms = sum(a.elapsed_time(b) for evs in bwd_events for a, b in evs) / (args.steps * nl)
 
     # forward kernel alone (outside the timed region, same buffers)
@@ -387,7 +391,8 @@ def run_ours(args, cfg):
     e_v = 2 if cfg["dtype"] == "bf16" else 4
     b_fwd, b_bwd = algorithmic_bytes(N, S, L, Lq, e_v)
     step_bytes = (b_fwd + b_bwd) * nl
-    value = world * step_bytes / (ms_step * 1e-3) / 1e9
+    # all ranks' bytes over the slowest rank's time
+    value = dist_utils.aggregate_throughput(step_bytes, ms_step_local * 1e-3, device) / 1e9
     peak, peak_src = measured_peak_gbs()
     bwd_gbs = b_bwd / (bwd_kernel_ms * 1e-3) / 1e9
     traffic = None

@@ -172,18 +172,54 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             }
           }
         };
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-          const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+        // SHARE: the 4 lanes of a row group hold the same 4 points; lane j locates point j only (cell, neighbour mask,
+        // padding test) and the results travel by width-4 shuffles inside the point loop -- a quarter of the scalar
+        // geometry per lane (it was 12 % of this kernel's instructions, all of it computed four times).  Measured: fp32 rows
+        // -1 % (cfg-1 2.02 -> 2.00 ms, cfg-3 1.034 -> 1.025 ms per step); 16-bit rows +1 % (cfg-2 backward 0.750 -> 0.758
+        // ms: the six shuffles per point add latency to a kernel that is latency-sensitive at 16 warps per SM), so it is
+        // compiled for fp32 rows only.
+        constexpr bool SHARE = SPEC && P == 4 && LPG == 4 && sizeof(VT) == 4;   // fp32 rows only: see below
+        float my_lh = 0.f, my_lw = 0.f, my_aw = 0.f;
+        int my_h = 0, my_w = 0, my_mask = 0;              // bit 4 of my_mask: the sample is accepted (cuh:288)
+        if constexpr (SHARE) {
+          const float px = j == 0 ? xy[0] : (j == 1 ? xy[2] : (j == 2 ? xy[4] : xy[6]));
+          const float py = j == 0 ? xy[1] : (j == 1 ? xy[3] : (j == 2 ? xy[5] : xy[7]));
+          const float pa = j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]));
+          const Cell<float> c = locate(px, py, H, W);
           const bool in = act && c.inside;
           int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          if constexpr (SPEC) {       // see msda_fwd.cu
-            if (pr.pad_mask != nullptr && mask != 0)
-              mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          if (pr.pad_mask != nullptr && mask != 0)
+            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          my_mask = mask | (in ? 16 : 0);
+          my_lh = in ? c.lh : 0.f; my_lw = in ? c.lw : 0.f; my_aw = in ? pa : 0.f;
+          my_h = c.h_low; my_w = c.w_low;
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          Cell<float> c;
+          bool in;
+          int mask;
+          if constexpr (SHARE) {
+            const int m5 = __shfl_sync(0xffffffffu, my_mask, p, 4);
+            c.h_low = __shfl_sync(0xffffffffu, my_h, p, 4);
+            c.w_low = __shfl_sync(0xffffffffu, my_w, p, 4);
+            g_lh[p] = __shfl_sync(0xffffffffu, my_lh, p, 4);
+            g_lw[p] = __shfl_sync(0xffffffffu, my_lw, p, 4);
+            g_aw[p] = __shfl_sync(0xffffffffu, my_aw, p, 4);
+            in = (m5 & 16) != 0;
+            mask = m5 & 15;
+          } else {
+            c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+            in = act && c.inside;
+            mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+            if constexpr (SPEC) {       // see msda_fwd.cu
+              if (pr.pad_mask != nullptr && mask != 0)
+                mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+            }
+            g_lh[p] = in ? c.lh : 0.f;
+            g_lw[p] = in ? c.lw : 0.f;
+            g_aw[p] = in ? a[p] : 0.f;
           }
-          g_lh[p] = in ? c.lh : 0.f;
-          g_lw[p] = in ? c.lw : 0.f;
-          g_aw[p] = in ? a[p] : 0.f;
           const float hh = 1.f - g_lh[p], hw = 1.f - g_lw[p];
           const float ah = hh * g_aw[p], al = g_lh[p] * g_aw[p];
           const float cw[4] = {ah * hw, ah * g_lw[p], al * hw, al * g_lw[p]};

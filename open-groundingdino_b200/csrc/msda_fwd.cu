@@ -123,6 +123,28 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         const VT *slab = value + (long long)(it.b * pr.S + tb.start[lc]) * MD + (it.m * D + j * CH);
         const int WMD = W * MD;
 
+        // SHARE: the 4 lanes of a row group hold the same 4 points; lane j locates point j only and computes its four
+        // weights, the results travel by width-4 shuffles (see msda_bwd.cu)
+        constexpr bool SHARE = SPEC && P == 4 && LPG == 4 && sizeof(VT) == 4;   // fp32 rows only: see below
+        float my_w[4] = {0.f, 0.f, 0.f, 0.f};
+        int my_off = 0, my_mask = 0;
+        if constexpr (SHARE) {
+          const float px = j == 0 ? xy[0] : (j == 1 ? xy[2] : (j == 2 ? xy[4] : xy[6]));
+          const float py = j == 0 ? xy[1] : (j == 1 ? xy[3] : (j == 2 ? xy[5] : xy[7]));
+          const float pa = j == 0 ? a[0] : (j == 1 ? a[1] : (j == 2 ? a[2] : a[3]));
+          const Cell<float> c = locate(px, py, H, W);
+          const bool in = act && c.inside;
+          int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+          if (pr.pad_mask != nullptr && mask != 0)
+            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          const float aw = in ? pa : 0.f;
+          const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;      // keeps NaN coordinates out
+          const float hh = 1.f - lh, hw = 1.f - lw;
+          const float ah = hh * aw, al = lh * aw;
+          my_w[0] = ah * hw; my_w[1] = ah * lw; my_w[2] = al * hw; my_w[3] = al * lw;
+          my_off = c.h_low * WMD + c.w_low * MD;
+          my_mask = mask;
+        }
 #pragma unroll
         for (int p0 = 0; p0 < P; p0 += PB) {
           typename Chan<VT>::Raw raw[PB][4];
@@ -130,19 +152,28 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
 #pragma unroll
           for (int pp = 0; pp < PB; ++pp) {
             const int p = p0 + pp;
-            const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
-            const bool in = act && c.inside;
-            int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-            if constexpr (SPEC) {     // the model's own geometry only: in the generic instantiations the extra live values spill
-              if (pr.pad_mask != nullptr && mask != 0)
-                mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+            int mask;
+            const VT *p00;
+            if constexpr (SHARE) {
+              mask = __shfl_sync(0xffffffffu, my_mask, p, 4);
+              p00 = slab + __shfl_sync(0xffffffffu, my_off, p, 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) wt[pp][kk] = __shfl_sync(0xffffffffu, my_w[kk], p, 4);
+            } else {
+              const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+              const bool in = act && c.inside;
+              mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+              if constexpr (SPEC) {   // the model's own geometry only: in the generic instantiations the extra live values spill
+                if (pr.pad_mask != nullptr && mask != 0)
+                  mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+              }
+              const float aw = in ? a[p] : 0.f;
+              const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
+              const float hh = 1.f - lh, hw = 1.f - lw;
+              const float ah = hh * aw, al = lh * aw;
+              wt[pp][0] = ah * hw; wt[pp][1] = ah * lw; wt[pp][2] = al * hw; wt[pp][3] = al * lw;
+              p00 = slab + (c.h_low * WMD + c.w_low * MD);
             }
-            const float aw = in ? a[p] : 0.f;
-            const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
-            const float hh = 1.f - lh, hw = 1.f - lw;
-            const float ah = hh * aw, al = lh * aw;
-            wt[pp][0] = ah * hw; wt[pp][1] = ah * lw; wt[pp][2] = al * hw; wt[pp][3] = al * lw;
-            const VT *p00 = slab + (c.h_low * WMD + c.w_low * MD);
             // fp32 only: measured +6-14 % there, -5-10 % for bf16 (the branch costs more than the zero fill)
             if (sizeof(VT) == 4 && mask == 15) {   // interior cell (the common case): plain loads, no predicates
               raw[pp][0] = Chan<VT>::gather_plain(p00);
