@@ -355,3 +355,23 @@ def test_deterministic_mode_unnormalised_attention_weights():
     truth_gv = oracle.backward(*args, g["grad_out"], np.float64)[0]
     gv = run_cuda(g, torch.float32, mode=1)[1]
     assert_close("grad_value (deterministic, attn x 4096)", gv, truth_gv, FP32_TOL)
+
+
+@pytest.mark.parametrize("M", [8, 5])
+@pytest.mark.parametrize("L", [1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_tile_kernels_level_and_head_counts(dtype, L, M):
+    """The query-tile kernels (csrc/msda_tile.cu) map a thread to a (query, level): fewer than 4 levels leave threads idle,
+    head counts other than 8 change the row pitch, tiles at the image border are partly empty (37 x 53 is no multiple of
+    8), and windows of coarse levels are clipped.  Forward (default in tile order) and the opt-in tile backward against the
+    fp64 oracle, distributions with and without locality."""
+    shapes = [(37, 53), (19, 27), (10, 14), (5, 7)][:L]
+    rnd = {torch.float32: lambda x: x, torch.bfloat16: oracle.bf16_round, torch.float16: _fp16_round}[dtype]
+    tol = {torch.float32: FP32_TOL, torch.bfloat16: BF16_TOL, torch.float16: 2e-3}[dtype]
+    for dist in ("I", "W"):
+        g = make_inputs(shapes, N=2, M=M, D=32, Lq=None, P=4, dist=dist, seed=10 * L + M)
+        g["value"] = rnd(g["value"]); g["grad_out"] = rnd(g["grad_out"])
+        args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
+        truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
+        for code in (3, 3 | 0x800):
+            check_all(g, run_cuda(g, dtype, code), truth, tol)
