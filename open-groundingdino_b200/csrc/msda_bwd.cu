@@ -53,7 +53,9 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 
 // ABL: ablation for profiling only (0 = the real kernel, 1 = reductions suppressed, 2 = value gathers suppressed)
 // SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
-template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0, bool SPEC = false>
+// MASK: input_padding_mask folded in (fused entry points with a mask only; section 5f of DESIGN.md).  A template parameter
+// and not a run-time test: even the never-taken `pad_mask != nullptr` branch per point cost this kernel 6 % (0.750 -> 0.794 ms).
+template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0, bool SPEC = false, bool MASK = false>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr_in) {
   Problem pr = pr_in;
   if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; pr.acc_permuted = 0; }
@@ -175,10 +177,11 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         // SHARE: the 4 lanes of a row group hold the same 4 points; lane j locates point j only (cell, neighbour mask,
         // padding test) and the results travel by width-4 shuffles inside the point loop -- a quarter of the scalar
         // geometry per lane (it was 12 % of this kernel's instructions, all of it computed four times).  Measured: fp32 rows
-        // -1 % (cfg-1 2.02 -> 2.00 ms, cfg-3 1.034 -> 1.025 ms per step); 16-bit rows +1 % (cfg-2 backward 0.750 -> 0.758
-        // ms: the six shuffles per point add latency to a kernel that is latency-sensitive at 16 warps per SM), so it is
-        // compiled for fp32 rows only.
-        constexpr bool SHARE = SPEC && P == 4 && LPG == 4 && sizeof(VT) == 4;   // fp32 rows only: see below
+        // -1 % (cfg-1 2.02 -> 2.00 ms, cfg-3 1.034 -> 1.025 ms per step); 16-bit rows +0.8 % at cfg-2 (752.7 -> 759.0 us)
+        // and +3 % at the decoder shape (87.3 -> 90.2 us) in a same-box A/B of two builds -- the six shuffles per point add
+        // latency to a kernel that is latency-sensitive at 16 warps per SM -- so it is compiled for fp32 rows only (the
+        // forward kernel uses it for every dtype).
+        constexpr bool SHARE = SPEC && P == 4 && LPG == 4 && sizeof(VT) == 4;
         float my_lh = 0.f, my_lw = 0.f, my_aw = 0.f;
         int my_h = 0, my_w = 0, my_mask = 0;              // bit 4 of my_mask: the sample is accepted (cuh:288)
         if constexpr (SHARE) {
@@ -188,8 +191,9 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
           const Cell<float> c = locate(px, py, H, W);
           const bool in = act && c.inside;
           int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          if (pr.pad_mask != nullptr && mask != 0)
-            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          if constexpr (MASK) {
+            if (mask != 0) mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          }
           my_mask = mask | (in ? 16 : 0);
           my_lh = in ? c.lh : 0.f; my_lw = in ? c.lw : 0.f; my_aw = in ? pa : 0.f;
           my_h = c.h_low; my_w = c.w_low;
@@ -212,9 +216,8 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
             c = locate(xy[2 * p], xy[2 * p + 1], H, W);
             in = act && c.inside;
             mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-            if constexpr (SPEC) {       // see msda_fwd.cu
-              if (pr.pad_mask != nullptr && mask != 0)
-                mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+            if constexpr (MASK) {
+              if (mask != 0) mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
             }
             g_lh[p] = in ? c.lh : 0.f;
             g_lw[p] = in ? c.lw : 0.f;
@@ -416,7 +419,9 @@ static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
     const bool spec = pr.L == 4 && pr.M == 8;
 #define MSDA_FUSED(CODE, PREV)                                                                          \
     if (minb == CODE) {                                                                                   \
-      if (spec) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true><<<grid, kThreads, 0, stream>>>(pr);           \
+      if (spec && pr.pad_mask != nullptr) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true, true><<<grid, kThreads, 0, stream>>>(pr);   \
+      else if (pr.pad_mask != nullptr) return MSDA_E_UNSUPPORTED;                                        \
+      else if (spec) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true><<<grid, kThreads, 0, stream>>>(pr);      \
       else bwd_vec_kernel<VT, D, P, 2, 0, PREV><<<grid, kThreads, 0, stream>>>(pr);                      \
       return (int)cudaGetLastError();                                                                     \
     }

@@ -24,7 +24,8 @@ namespace msda {
 // PB = points whose 4 gathers are in flight together (register staging: PB*16 registers)
 // SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
 // ST: stage the next unit's positions / weights with cp.async (model-geometry kernels in linear query order)
-template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false, bool ST = false>
+// MASK: input_padding_mask folded in (fused entry points with a mask only); a template parameter, see msda_bwd.cu
+template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false, bool ST = false, bool MASK = false>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr_in) {
   Problem pr = pr_in;
   if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; }
@@ -124,8 +125,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
         const int WMD = W * MD;
 
         // SHARE: the 4 lanes of a row group hold the same 4 points; lane j locates point j only and computes its four
-        // weights, the results travel by width-4 shuffles (see msda_bwd.cu)
-        constexpr bool SHARE = SPEC && P == 4 && LPG == 4 && sizeof(VT) == 4;   // fp32 rows only: see below
+        // weights, the results travel by width-4 shuffles.  Same-box A/B (two builds, tools/sweep.py): decoder forward
+        // bf16 33.3 -> 31.4 us, fp32 46.2 -> 45.9 us per layer.
+        constexpr bool SHARE = SPEC && P == 4 && LPG == 4;
         float my_w[4] = {0.f, 0.f, 0.f, 0.f};
         int my_off = 0, my_mask = 0;
         if constexpr (SHARE) {
@@ -135,8 +137,9 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
           const Cell<float> c = locate(px, py, H, W);
           const bool in = act && c.inside;
           int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-          if (pr.pad_mask != nullptr && mask != 0)
-            mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          if constexpr (MASK) {
+            if (mask != 0) mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+          }
           const float aw = in ? pa : 0.f;
           const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;      // keeps NaN coordinates out
           const float hh = 1.f - lh, hw = 1.f - lw;
@@ -163,9 +166,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem p
               const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
               const bool in = act && c.inside;
               mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
-              if constexpr (SPEC) {   // the model's own geometry only: in the generic instantiations the extra live values spill
-                if (pr.pad_mask != nullptr && mask != 0)
-                  mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
+              if constexpr (MASK) {
+                if (mask != 0) mask = drop_padded(pr.pad_mask, mask, it.b * pr.S + tb.start[lc] + c.h_low * W + c.w_low, W);
               }
               const float aw = in ? a[p] : 0.f;
               const float lh = in ? c.lh : 0.f, lw = in ? c.lw : 0.f;    // keeps NaN coordinates out
@@ -229,7 +231,9 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
     const bool spec = pr.L == 4 && pr.M == 8;
 #define MSDA_FUSED(CODE, PREV)                                                                          \
     if (minb == CODE) {                                                                                   \
-      if (spec) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true><<<grid, kThreads, 0, stream>>>(pr);         \
+      if (spec && pr.pad_mask != nullptr) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true, false, true><<<grid, kThreads, 0, stream>>>(pr);   \
+      else if (pr.pad_mask != nullptr) return MSDA_E_UNSUPPORTED;                                        \
+      else if (spec) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true><<<grid, kThreads, 0, stream>>>(pr);    \
       else fwd_vec_kernel<VT, D, P, 3, PB3, PREV><<<grid, kThreads, 0, stream>>>(pr);                    \
       return (int)cudaGetLastError();                                                                     \
     }

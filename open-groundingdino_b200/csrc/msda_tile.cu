@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
           const bool on = (mask >> kk) & 1;
           const float w = on ? cw[kk] : 0.f;
           // a zero weight needs no row: 0 * row is 0 for every finite row
-          const unsigned o = (on && w != 0.f) ? (unsigned)((r * pr.M + it.m) * D) : kNoLoad;
-          my[p * 4 + kk] = make_int2((int)o, __float_as_int(w));
+          const int o = (on && w != 0.f) ? (r * pr.M + it.m) * D : -1;           // negative: no row behind this record
+          my[p * 4 + kk] = make_int2(o, __float_as_int(w));
         }
       }
     }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
             const int s = s0 + u;
             const int2 r = rp[(s >> 2) * kRecStride + (s & 3) * 4];
             w[u] = __int_as_float(r.y);
-            raw[u] = Chan<VT>::gather(vbase + ((unsigned)r.x & kOffMask), ((unsigned)r.x & kNoLoad) == 0u);
+            raw[u] = Chan<VT>::gather(vbase + r.x, r.x >= 0);
           }
 #pragma unroll
           for (int u = 0; u < RB; ++u) {

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libmsda_b200.so")
+# MSDA_B200_LIB: another build of the same library (A/B measurements of compile-time switches)
+LIB_PATH = os.environ.get("MSDA_B200_LIB") or os.path.join(_PKG_DIR, "libmsda_b200.so")
 
 MSDA_F32, MSDA_BF16, MSDA_F64, MSDA_F16 = 0, 1, 2, 3
 MSDA_BWD_ATOMIC, MSDA_BWD_DETERMINISTIC = 0, 1
