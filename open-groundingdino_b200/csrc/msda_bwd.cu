@@ -57,6 +57,7 @@ __device__ __forceinline__ void reduce_scatter(float *d, int j) {
 // and not a run-time test: even the never-taken `pad_mask != nullptr` branch per point cost this kernel 6 % (0.750 -> 0.794 ms).
 template <typename VT, int D, int P, int MINB, int ABL = 0, int PRE = 0, bool SPEC = false, bool MASK = false>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem pr_in) {
+  pdl_wait();
   Problem pr = pr_in;
   if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; pr.acc_permuted = 0; }
   constexpr int CH = Chan<VT>::kPerLane;
@@ -419,32 +420,32 @@ static int launch_bwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
     const bool spec = pr.L == 4 && pr.M == 8;
 #define MSDA_FUSED(CODE, PREV)                                                                          \
     if (minb == CODE) {                                                                                   \
-      if (spec && pr.pad_mask != nullptr) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true, true><<<grid, kThreads, 0, stream>>>(pr);   \
+      if (spec && pr.pad_mask != nullptr) launch_pdl(bwd_vec_kernel<VT, D, P, 2, 0, PREV, true, true>, grid, kThreads, 0, stream, pr);   \
       else if (pr.pad_mask != nullptr) return MSDA_E_UNSUPPORTED;                                        \
-      else if (spec) bwd_vec_kernel<VT, D, P, 2, 0, PREV, true><<<grid, kThreads, 0, stream>>>(pr);      \
-      else bwd_vec_kernel<VT, D, P, 2, 0, PREV><<<grid, kThreads, 0, stream>>>(pr);                      \
+      else if (spec) launch_pdl(bwd_vec_kernel<VT, D, P, 2, 0, PREV, true>, grid, kThreads, 0, stream, pr);      \
+      else launch_pdl(bwd_vec_kernel<VT, D, P, 2, 0, PREV>, grid, kThreads, 0, stream, pr);                      \
       return (int)cudaGetLastError();                                                                     \
     }
     MSDA_FUSED(201, 1) MSDA_FUSED(202, 2) MSDA_FUSED(203, 3)
 #undef MSDA_FUSED
 #ifdef MSDA_BUILD_VARIANTS      // profiling ablations (variant bits 6..7)
-    if (minb == 101) { bwd_vec_kernel<VT, D, P, 2, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-    if (minb == 102) { bwd_vec_kernel<VT, D, P, 2, 2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+    if (minb == 101) { launch_pdl(bwd_vec_kernel<VT, D, P, 2, 1>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
+    if (minb == 102) { launch_pdl(bwd_vec_kernel<VT, D, P, 2, 2>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
 #endif
   }
   if (minb >= 100) return MSDA_E_UNSUPPORTED;
   if constexpr (D == 32 && P == 4) {
     if (minb == 2 && pr.L == 4 && pr.M == 8) {
-      bwd_vec_kernel<VT, D, P, 2, 0, 0, true><<<grid, kThreads, 0, stream>>>(pr);
+      launch_pdl(bwd_vec_kernel<VT, D, P, 2, 0, 0, true>, grid, kThreads, 0, stream, pr);
       return (int)cudaGetLastError();
     }
   }
 #ifdef MSDA_BUILD_VARIANTS      // occupancy experiments (variant bits 4..5): 3 and 4 CTAs per SM spill and lose (tools/sweep.py)
-  if (minb == 4) { bwd_vec_kernel<VT, D, P, 4><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-  if (minb == 3) { bwd_vec_kernel<VT, D, P, 3><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+  if (minb == 4) { launch_pdl(bwd_vec_kernel<VT, D, P, 4>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
+  if (minb == 3) { launch_pdl(bwd_vec_kernel<VT, D, P, 3>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
 #endif
   if (minb != 2) return MSDA_E_UNSUPPORTED;
-  bwd_vec_kernel<VT, D, P, 2><<<grid, kThreads, 0, stream>>>(pr);
+  launch_pdl(bwd_vec_kernel<VT, D, P, 2>, grid, kThreads, 0, stream, pr);
   return (int)cudaGetLastError();
 }
 

@@ -201,6 +201,14 @@ __device__ __forceinline__ WorkItem work_item(const Tables &tb, int passes_per_u
   return wi;
 }
 
+// Programmatic dependent launch (launch_pdl in msda_launch.h): block until the previous kernel of the stream has completed
+// and flushed, then let the next kernel of the stream be scheduled as this one's CTAs retire.  A no-op in a kernel that
+// was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---- sampler geometry --------------------------------------------------------------------------
 template <typename T>
 struct Cell {

@@ -27,6 +27,7 @@ namespace msda {
 // MASK: input_padding_mask folded in (fused entry points with a mask only); a template parameter, see msda_bwd.cu
 template <typename VT, int D, int P, int MINB, int PB, int PRE = 0, bool SPEC = false, bool ST = false, bool MASK = false>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_vec_kernel(const Problem pr_in) {
+  pdl_wait();
   Problem pr = pr_in;
   if constexpr (SPEC) { pr.L = 4; pr.M = 8; pr.tile_w_log2 = 3; }
   constexpr int CH = Chan<VT>::kPerLane;   // channels per lane
@@ -231,10 +232,10 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
     const bool spec = pr.L == 4 && pr.M == 8;
 #define MSDA_FUSED(CODE, PREV)                                                                          \
     if (minb == CODE) {                                                                                   \
-      if (spec && pr.pad_mask != nullptr) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true, false, true><<<grid, kThreads, 0, stream>>>(pr);   \
+      if (spec && pr.pad_mask != nullptr) launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true, false, true>, grid, kThreads, 0, stream, pr);   \
       else if (pr.pad_mask != nullptr) return MSDA_E_UNSUPPORTED;                                        \
-      else if (spec) fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true><<<grid, kThreads, 0, stream>>>(pr);    \
-      else fwd_vec_kernel<VT, D, P, 3, PB3, PREV><<<grid, kThreads, 0, stream>>>(pr);                    \
+      else if (spec) launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3, PREV, true>, grid, kThreads, 0, stream, pr);    \
+      else launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3, PREV>, grid, kThreads, 0, stream, pr);                    \
       return (int)cudaGetLastError();                                                                     \
     }
     MSDA_FUSED(201, 1) MSDA_FUSED(202, 2) MSDA_FUSED(203, 3)
@@ -243,19 +244,19 @@ static int launch_fwd_vec(const Problem &pr, int grid, int minb, cudaStream_t st
   if (minb > 200) return MSDA_E_UNSUPPORTED;
   if constexpr (D == 32 && P == 4) {
     if (minb == 3 && pr.L == 4 && pr.M == 8) {
-      if (pr.tiled) fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, false><<<grid, kThreads, 0, stream>>>(pr);
-      else fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, true><<<grid, kThreads, 0, stream>>>(pr);
+      if (pr.tiled) launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, false>, grid, kThreads, 0, stream, pr);
+      else launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3, 0, true, true>, grid, kThreads, 0, stream, pr);
       return (int)cudaGetLastError();
     }
   }
 #ifdef MSDA_BUILD_VARIANTS      // occupancy experiments (variant bits 4..5); the product build carries the measured best only
-  if (minb == 4) { fwd_vec_kernel<VT, D, P, 4, 1><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
-  if (minb == 2) { fwd_vec_kernel<VT, D, P, 2, PB2><<<grid, kThreads, 0, stream>>>(pr); return (int)cudaGetLastError(); }
+  if (minb == 4) { launch_pdl(fwd_vec_kernel<VT, D, P, 4, 1>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
+  if (minb == 2) { launch_pdl(fwd_vec_kernel<VT, D, P, 2, PB2>, grid, kThreads, 0, stream, pr); return (int)cudaGetLastError(); }
 #else
   (void)PB2;
 #endif
   if (minb != 3) return MSDA_E_UNSUPPORTED;
-  fwd_vec_kernel<VT, D, P, 3, PB3><<<grid, kThreads, 0, stream>>>(pr);
+  launch_pdl(fwd_vec_kernel<VT, D, P, 3, PB3>, grid, kThreads, 0, stream, pr);
   return (int)cudaGetLastError();
 }
 

@@ -141,6 +141,7 @@ struct RowBatch {   // row gathers kept in flight per lane in the row loops (reg
 // ================================================================================================ forward
 template <typename VT, int PRE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem pr) {
+  pdl_wait();
   constexpr int D = 32, CH = 8, NP = 4;
   static_assert(Chan<VT>::kPerLane == CH && Chan<VT>::kPairs == NP, "8 channels per lane");
   extern __shared__ __align__(16) unsigned char smem[];
@@ -323,6 +324,7 @@ __device__ __forceinline__ void coop_row_reduce(float *gbase, bool first, float 
 //   C   grad_sampling_loc / grad_attn_weight per (query, level) thread from the 16 dot products, 16-byte stores.
 template <typename VT, int PRE>
 __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr) {
+  pdl_wait();
   constexpr int D = 32, CH = 8, NP = 4;
   static_assert(Chan<VT>::kPerLane == CH && Chan<VT>::kPairs == NP, "8 channels per lane");
   extern __shared__ __align__(16) unsigned char smem[];
@@ -677,7 +679,7 @@ int launch_fwd(const Problem &pr, int sms, int minb, int pre, cudaStream_t strea
 #define MSDA_TILE_FWD(PREV, MB)                                                      \
   if (pre == PREV && minb == MB) {                                                   \
     if (int rc = set_smem(fwd_tile_kernel<VT, PREV, MB>, kFwdSmem)) return rc;       \
-    fwd_tile_kernel<VT, PREV, MB><<<sms * MB, kThreads, kFwdSmem, stream>>>(pr);     \
+    launch_pdl(fwd_tile_kernel<VT, PREV, MB>, sms * MB, kThreads, kFwdSmem, stream, pr);     \
     return (int)cudaGetLastError();                                                  \
   }
   MSDA_TILE_FWD(0, 3) MSDA_TILE_FWD(1, 3) MSDA_TILE_FWD(2, 3) MSDA_TILE_FWD(3, 3)
@@ -693,7 +695,7 @@ int launch_bwd(const Problem &pr, int grid, int pre, cudaStream_t stream) {
 #define MSDA_TILE_BWD(PREV)                                                          \
   if (pre == PREV) {                                                                 \
     if (int rc = set_smem(bwd_tile_kernel<VT, PREV>, kBwdSmem)) return rc;           \
-    bwd_tile_kernel<VT, PREV><<<grid, kThreads, kBwdSmem, stream>>>(pr);             \
+    launch_pdl(bwd_tile_kernel<VT, PREV>, grid, kThreads, kBwdSmem, stream, pr);             \
     return (int)cudaGetLastError();                                                  \
   }
   MSDA_TILE_BWD(0)       // the op boundary only: this kernel is the measured alternative, not the default (see msda_api.cu)
