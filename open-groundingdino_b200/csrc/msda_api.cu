@@ -120,7 +120,7 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
   const int family = pick_family(variant, dtype, D, P, L, Lq, S, al);
   if (family == 1) return launch_forward_generic(pr, dtype, stream);
   pr.tiled = (family == 3);
-  if (use_tile_kernels(variant, family, dtype, pr)) return launch_forward_tile(pr, dtype, sm_count(), min_blocks(variant, 3), 0, stream);
+  if (use_tile_kernels(variant, family, dtype, pr)) return launch_forward_tile(pr, dtype, sm_count(), 0, stream);
   return launch_forward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 3)), min_blocks(variant, 3), stream);
 }
 
@@ -231,7 +231,7 @@ int msda_fused_forward_masked(const void *value, const unsigned char *padding_ma
   pr.tiled = ((variant & 15) == 2) ? 0 : (Lq == S);
   const int pre = q_dtype == MSDA_BF16 ? 2 : q_dtype == MSDA_F16 ? 3 : 1;
   if (use_tile_kernels(variant, pr.tiled ? 3 : 2, dtype, pr))
-    return launch_forward_tile(pr, dtype, sm_count(), 3, pre, static_cast<cudaStream_t>(stream_));
+    return launch_forward_tile(pr, dtype, sm_count(), pre, static_cast<cudaStream_t>(stream_));
   return launch_forward_vec(pr, dtype, vec_grid(pr, 3), 200 + pre, static_cast<cudaStream_t>(stream_));
 }
 

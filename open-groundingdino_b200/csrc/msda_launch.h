@@ -34,7 +34,7 @@ int launch_backward_vec(const Problem &pr, int dtype, int grid, int min_blocks, 
 
 // query-tile kernels (msda_tile.cu): encoder self-attention, D = 32, P = 4, L <= 4; `pre` as in msda_pre.cuh
 bool tile_supported(int dtype, int N, int S, int M, int D, int L, int P);
-int launch_forward_tile(const Problem &pr, int dtype, int sms, int min_blocks, int pre, cudaStream_t stream);
+int launch_forward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream);
 int launch_backward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream);
 
 // generic per-channel kernels (any D, P, L; fp32 / fp64 / bf16 value)

@@ -133,8 +133,17 @@ __device__ __forceinline__ Sample make_sample(float x, float y, float a, bool ac
   return s;
 }
 
+// Occupancy and gather batching of the tile forward, from a same-box A/B of builds (cfg-2 bf16 / cfg-1 fp32, us per layer):
+// 16-bit rows: 2 CTAs/SM x 8 gathers in flight 299.8, 3 x 4 271.1, 4 x 4 257.2, 4 x 2 257.0, 4 x 8 (spills) 271.5, 5 x 4 259.3,
+// 6 x 2 262.2; software-pipelined batches no better.  fp32 rows (8 registers per gather): 3 x 2 103.4, 3 x 4 100.7, 4 x 2 106.6.
+template <typename VT>
+struct TileFwdCfg {
+  static constexpr bool wide = sizeof(typename Chan<VT>::Raw) != 16;
+  static constexpr int minb = wide ? 3 : 4;      // resident CTAs per SM the kernel is register-limited for
+  static constexpr int rb = 4;                   // row gathers kept in flight per lane
+};
 template <typename VT, int MINB>
-struct RowBatch {   // row gathers kept in flight per lane in the row loops (registers: 4 or 8 per gather)
+struct RowBatch {   // backward: row gathers kept in flight per lane in the direct path (registers: 4 or 8 per gather)
   static constexpr int value = (sizeof(typename Chan<VT>::Raw) == 16 ? 8 : 4) / (MINB >= 3 ? 2 : 1);
 };
 
@@ -146,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
   static_assert(Chan<VT>::kPerLane == CH && Chan<VT>::kPairs == NP, "8 channels per lane");
   extern __shared__ __align__(16) unsigned char smem[];
   Tables &tb = *reinterpret_cast<Tables *>(smem);
+  int *itab = reinterpret_cast<int *>(smem + kTablesBytes + (size_t)kRecs * sizeof(int2));   // [64] output row of every query, -1 = none
   int2 *rb = reinterpret_cast<int2 *>(smem + kTablesBytes);        // [kRecs] {offset | flags, weight}; single copy: with
   // two copies (one barrier per unit) three resident CTAs leave the SM 28 KB of L1 for the gathers
   load_tables(pr, tb, kTileItems);
@@ -167,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
       thread_level_inputs<PRE>(pr, it, lc, act, H, W, xy, a, sc);
       const int rowbase = it.b * pr.S + tb.start[lc];
       int2 *my = rb + t * kRecStride;
+      if (l == 0) itab[k] = it.valid ? it.item : -1;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const Sample s = make_sample(xy[2 * p], xy[2 * p + 1], a[p], act, H, W, rowbase);
@@ -190,11 +201,11 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
     {  // ---- row loop: two queries per warp (half-warps), group = neighbour, lane = 8 channels
       const int half = lane >> 4, kk = (lane >> 2) & 3, j = lane & 3;
       const VT *vbase = value + j * CH;
-      constexpr int RB = RowBatch<VT, MINB>::value;
+      constexpr int RB = TileFwdCfg<VT>::rb;
 #pragma unroll 1
       for (int pair = 0; pair < 4; ++pair) {
         const int k = warp * 8 + pair * 2 + half;
-        const Item it = decode_item(pr, tb, uc, k);
+        const int out_item = itab[k];
         const int2 *rp = rb + (k * 4) * kRecStride + kk;
         unsigned long long acc[NP] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
@@ -220,12 +231,37 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
         float res[CH];
 #pragma unroll
         for (int c = 0; c < NP; ++c) unpack_f2(acc[c], res[2 * c], res[2 * c + 1]);
+        {   // reduce-scatter over the 4 neighbour groups (6 shuffles instead of 16): every group ends with 2 of the lane's 8
+            // channels and stores them (same-box A/B with the query table above: 257.4 -> 255.5 us, U 277.5 -> 272.3 us)
+          const bool up1 = (kk & 1) != 0;
+          float h[4];
 #pragma unroll
-        for (int d = 4; d <= 8; d <<= 1) {
+          for (int c = 0; c < 4; ++c) {
+            const float send = up1 ? res[c] : res[c + 4];
+            const float keep = up1 ? res[c + 4] : res[c];
+            h[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          const bool up2 = (kk & 2) != 0;
+          float q[2];
 #pragma unroll
-          for (int c = 0; c < CH; ++c) res[c] += __shfl_xor_sync(0xffffffffu, res[c], d);
+          for (int c = 0; c < 2; ++c) {
+            const float send = up2 ? h[c] : h[c + 2];
+            const float keep = up2 ? h[c + 2] : h[c];
+            q[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          // channels held: base = (up1 ? 4 : 0) + (up2 ? 2 : 0)
+          const int cbase = (up1 ? 4 : 0) + (up2 ? 2 : 0);
+          if (out_item >= 0) {
+            if constexpr (sizeof(VT) == 2 && !TileFwdCfg<VT>::wide) {
+              unsigned word;
+              if constexpr (__is_same(VT, __half)) word = Chan<__half>::pack2(q[0], q[1]);
+              else word = Chan<__nv_bfloat16>::pack2(q[0], q[1]);
+              *reinterpret_cast<unsigned *>(out + (long long)out_item * D + j * CH + cbase) = word;
+            } else {
+              *reinterpret_cast<float2 *>(reinterpret_cast<float *>(out) + (long long)out_item * D + j * CH + cbase) = make_float2(q[0], q[1]);
+            }
+          }
         }
-        if (it.valid && kk == 0) Chan<VT>::store(out + (long long)it.item * D + j * CH, Chan<VT>::pack(res));
       }
     }
     __syncthreads();     // the next unit's phase A overwrites the records
@@ -667,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr)
   }
 }
 
-constexpr size_t kFwdSmem = kTablesBytes + (size_t)kRecs * sizeof(int2);
+constexpr size_t kFwdSmem = kTablesBytes + (size_t)kRecs * sizeof(int2) + 256;
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
@@ -675,17 +711,14 @@ int set_smem(K kernel, size_t bytes) {
 }
 
 template <typename VT>
-int launch_fwd(const Problem &pr, int sms, int minb, int pre, cudaStream_t stream) {
-#define MSDA_TILE_FWD(PREV, MB)                                                      \
-  if (pre == PREV && minb == MB) {                                                   \
-    if (int rc = set_smem(fwd_tile_kernel<VT, PREV, MB>, kFwdSmem)) return rc;       \
-    launch_pdl(fwd_tile_kernel<VT, PREV, MB>, sms * MB, kThreads, kFwdSmem, stream, pr);     \
-    return (int)cudaGetLastError();                                                  \
+int launch_fwd(const Problem &pr, int sms, int pre, cudaStream_t stream) {
+  constexpr int MB = TileFwdCfg<VT>::minb;
+#define MSDA_TILE_FWD(PREV)                                                              \
+  if (pre == PREV) {                                                                     \
+    if (int rc = set_smem(fwd_tile_kernel<VT, PREV, MB>, kFwdSmem)) return rc;           \
+    return launch_pdl(fwd_tile_kernel<VT, PREV, MB>, sms * MB, kThreads, kFwdSmem, stream, pr);  \
   }
-  MSDA_TILE_FWD(0, 3) MSDA_TILE_FWD(1, 3) MSDA_TILE_FWD(2, 3) MSDA_TILE_FWD(3, 3)
-#ifdef MSDA_BUILD_VARIANTS
-  MSDA_TILE_FWD(0, 2)
-#endif
+  MSDA_TILE_FWD(0) MSDA_TILE_FWD(1) MSDA_TILE_FWD(2) MSDA_TILE_FWD(3)
 #undef MSDA_TILE_FWD
   return MSDA_E_UNSUPPORTED;
 }
@@ -712,16 +745,10 @@ bool tile_supported(int dtype, int N, int S, int M, int D, int L, int P) {
 }
 
 // pre: 0 = sampling locations / attention weights given; 1 / 2 / 3 = raw fp32 / bf16 / fp16 offsets and logits (msda_pre.cuh)
-// minb: resident CTAs per SM the kernel is compiled for (3 = default; 2 exists for the op boundary, A/B)
-int launch_forward_tile(const Problem &pr, int dtype, int sms, int minb, int pre, cudaStream_t stream) {
-#ifdef MSDA_BUILD_VARIANTS
-  if (pre != 0 || minb != 2) minb = 3;
-#else
-  minb = 3;
-#endif
-  if (dtype == MSDA_F32) return launch_fwd<wide_f32>(pr, sms, minb, pre, stream);
-  if (dtype == MSDA_BF16) return launch_fwd<__nv_bfloat16>(pr, sms, minb, pre, stream);
-  if (dtype == MSDA_F16) return launch_fwd<__half>(pr, sms, minb, pre, stream);
+int launch_forward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream) {
+  if (dtype == MSDA_F32) return launch_fwd<wide_f32>(pr, sms, pre, stream);
+  if (dtype == MSDA_BF16) return launch_fwd<__nv_bfloat16>(pr, sms, pre, stream);
+  if (dtype == MSDA_F16) return launch_fwd<__half>(pr, sms, pre, stream);
   return MSDA_E_UNSUPPORTED;
 }
 
