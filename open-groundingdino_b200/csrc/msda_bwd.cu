@@ -105,12 +105,12 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         OffsetScale sc;
         level_inputs<P, PRE>(pr, it, lc, act, H, W, LPG, LPG * GI, j, xy, a, sc);
         const long long row_off = (long long)(it.b * pr.S + tb.start[lc]) * MD + it.m * D;
-        const VT *slab = value + row_off + j * CH;
+        const VT *slab = as_given(value + row_off + j * CH);
         // fp32 accumulator row of this head.  fp32 value: natural channel order (it IS grad_value).
         // bf16 value: the row is stored as [first halves of every lane's 8 channels | second halves]
         // (acc_pos() in msda_common.cuh) so each 16-byte reduction of a 4-lane group lands in ONE
         // fully-used 64-byte span instead of half of every 32-byte sector.
-        float *gslab = gacc + row_off + (pr.acc_permuted ? j * 4 : j * CH);
+        float *gslab = as_given(gacc + row_off + (pr.acc_permuted ? j * 4 : j * CH));
         const int chunk_stride = pr.acc_permuted ? D / 2 : 4;     // second 4-channel chunk of a lane's 8
         const int WMD = W * MD;
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_vec_kernel(const Problem p
         const bool first = (lane & LPG) == 0;
         const unsigned long long gsel0 = (COOP && !first) ? go[NP / 2] : go[0];
         const unsigned long long gsel1 = (COOP && !first) ? go[NP / 2 + 1] : go[1];
-        float *gcoop = gacc + (long long)(it.b * pr.S) * MD + it.m * D + j * CH + (first ? 0 : 4);
+        float *gcoop = as_given(gacc + (long long)(it.b * pr.S) * MD + it.m * D + j * CH + (first ? 0 : 4));
         const int lvl_off = tb.start[lc] * MD;
         // one round of reductions of this group alone: coefficient e[kk] for the row at off + corner(kk); gslab-relative
         auto plain_emit = [&](const float (&e)[4], int off, int wmd) {

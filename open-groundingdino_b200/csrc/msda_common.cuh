@@ -315,6 +315,15 @@ __device__ __forceinline__ uint4 gather16(const void *p, bool pred) {
   return v;
 }
 
+// A pointer the compiler must take as given.  Left to itself it splits `base + row_off + lane part` back into the uniform
+// kernel-parameter base and a 64-bit index, and rebuilds EVERY address from them (sign extension + two 64-bit adds: four to five
+// ALU instructions per gather or reduction address); behind this fence an address is the pointer plus a 32-bit offset (two).
+template <typename T>
+__device__ __forceinline__ T *as_given(T *p) {
+  asm("" : "+l"(p));
+  return p;
+}
+
 // fp32 rows handled 8 channels (32 bytes) per lane: half the lanes per row, so a warp pass covers two items
 // and the per-item geometry / bookkeeping instructions halve (the fp32 kernels are issue-bound).
 struct wide_f32 {

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
     __syncthreads();
     {  // ---- row loop: two queries per warp (half-warps), group = neighbour, lane = 8 channels
       const int half = lane >> 4, kk = (lane >> 2) & 3, j = lane & 3;
-      const VT *vbase = value + j * CH;
+      const VT *vbase = as_given(value + j * CH);   // address = one IMAD.WIDE (msda_common.cuh)
       constexpr int RB = TileFwdCfg<VT>::rb;
 #pragma unroll 1
       for (int pair = 0; pair < 4; ++pair) {
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr)
     {  // ---- D: directly handled samples; warp step = 2 samples x 4 neighbours, lane = 8 channels of one row
       const int n_direct = misc[8 + parity];
       const bool first = (g & 1) == 0;
-      const VT *vbase = value + j * CH;
+      const VT *vbase = as_given(value + j * CH);   // address = one IMAD.WIDE (msda_common.cuh)
       float *gbase = gacc + j * CH;
       for (int i0 = warp * 2; i0 < n_direct; i0 += (kThreads / 32) * 2) {
         const int si = i0 + (g >> 2);
