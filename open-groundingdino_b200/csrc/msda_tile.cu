@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
         }
       }
     }
-    __syncthreads();
+    __syncwarp();        // a warp's row loop reads only what its own 32 (query, level) threads wrote: no block barrier
     {  // ---- row loop: two queries per warp (half-warps), group = neighbour, lane = 8 channels
       const int half = lane >> 4, kk = (lane >> 2) & 3, j = lane & 3;
       const VT *vbase = as_given(value + j * CH);   // address = one IMAD.WIDE (msda_common.cuh)
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, MINB) fwd_tile_kernel(const Problem 
         }
       }
     }
-    __syncthreads();     // the next unit's phase A overwrites the records
+    __syncwarp();        // the next unit's phase A overwrites the warp's records
   }
 }
 
