@@ -85,6 +85,7 @@ const char *msda_error_string(int code);
 #define MSDA_VARIANT_NO_NARROW 0x200
 #define MSDA_VARIANT_OLD_TILED 0x400
 #define MSDA_VARIANT_TILE_BWD 0x800
+#define MSDA_VARIANT_WARP_BWD 0x1000
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output,
                  int batch, int spatial_size, int num_heads, int channels, int num_levels,

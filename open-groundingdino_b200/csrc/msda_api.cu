@@ -179,7 +179,9 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     // The tile backward (counting sort + row-stationary pass, msda_tile.cu) is correct and sends 3x fewer reductions to
     // the L2, but measured slower than the row-group kernel (0.93 vs 0.75 ms at cfg-2, profiles/r02_tile_backward.md):
     // opt-in through MSDA_VARIANT_TILE_BWD.
-    if ((variant & MSDA_VARIANT_TILE_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
+    if ((variant & MSDA_VARIANT_WARP_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
+      rc = launch_backward_warp(pr, dtype, sm_count(), 0, stream);
+    else if ((variant & MSDA_VARIANT_TILE_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
       rc = launch_backward_tile(pr, dtype, sm_count(), 0, stream);
     else rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
   }

@@ -29,28 +29,6 @@
 
 namespace msda {
 
-// After the call lane j (0 <= j < LPG) holds the group sums of d[j*c .. j*c+c) in d[0..c), c = NV/LPG.
-// When NV < LPG the tail rounds degrade to plain all-reduces.
-template <int N, int DIST>
-__device__ __forceinline__ void reduce_scatter(float *d, int j) {
-  if constexpr (DIST >= 1) {
-    if constexpr (N >= 2) {
-      constexpr int HALF = N / 2;
-      const bool upper = (j & DIST) != 0;
-#pragma unroll
-      for (int i = 0; i < HALF; ++i) {
-        const float send = upper ? d[i] : d[i + HALF];
-        const float keep = upper ? d[i + HALF] : d[i];
-        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, DIST);
-      }
-      reduce_scatter<HALF, DIST / 2>(d, j);
-    } else {
-      d[0] += __shfl_xor_sync(0xffffffffu, d[0], DIST);
-      reduce_scatter<1, DIST / 2>(d, j);
-    }
-  }
-}
-
 // ABL: ablation for profiling only (0 = the real kernel, 1 = reductions suppressed, 2 = value gathers suppressed)
 // SPEC: the model's own geometry (L = 4 levels, M = 8 heads) as compile-time constants
 // MASK: input_padding_mask folded in (fused entry points with a mask only; section 5f of DESIGN.md).  A template parameter

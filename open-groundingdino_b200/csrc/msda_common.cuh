@@ -447,6 +447,28 @@ struct Chan<__half> {
   }
 };
 
+// After the call lane j (0 <= j < LPG) holds the group sums of d[j*c .. j*c+c) in d[0..c), c = NV/LPG.
+// When NV < LPG the tail rounds degrade to plain all-reduces.
+template <int N, int DIST>
+__device__ __forceinline__ void reduce_scatter(float *d, int j) {
+  if constexpr (DIST >= 1) {
+    if constexpr (N >= 2) {
+      constexpr int HALF = N / 2;
+      const bool upper = (j & DIST) != 0;
+#pragma unroll
+      for (int i = 0; i < HALF; ++i) {
+        const float send = upper ? d[i] : d[i + HALF];
+        const float keep = upper ? d[i + HALF] : d[i];
+        d[i] = keep + __shfl_xor_sync(0xffffffffu, send, DIST);
+      }
+      reduce_scatter<HALF, DIST / 2>(d, j);
+    } else {
+      d[0] += __shfl_xor_sync(0xffffffffu, d[0], DIST);
+      reduce_scatter<1, DIST / 2>(d, j);
+    }
+  }
+}
+
 // Vector reduction: one 16-byte fp32x4 add performed by the L2 atomic unit (REDG.E.ADD.F32x4).
 __device__ __forceinline__ void red_add_f32x4(float *p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)

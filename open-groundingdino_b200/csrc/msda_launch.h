@@ -36,6 +36,7 @@ int launch_backward_vec(const Problem &pr, int dtype, int grid, int min_blocks, 
 bool tile_supported(int dtype, int N, int S, int M, int D, int L, int P);
 int launch_forward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream);
 int launch_backward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream);
+int launch_backward_warp(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream);
 
 // generic per-channel kernels (any D, P, L; fp32 / fp64 / bf16 value)
 int launch_forward_generic(const Problem &pr, int dtype, cudaStream_t stream);

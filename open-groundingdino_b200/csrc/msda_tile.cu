@@ -111,6 +111,59 @@ __device__ __forceinline__ void thread_level_inputs(const Problem &pr, const Ite
   }
 }
 
+// grad_sampling_loc / grad_attn_weight of one (query, level), or with the fused pre-op the gradients of the raw offsets and
+// logits (softmax backward across the query's four level threads: every thread of the warp must call this).
+template <int PRE>
+__device__ __forceinline__ void store_small_grads(const Problem &pr, const Item &it, int lc, bool act, const float (&a)[4],
+                                                  const OffsetScale &sc, const float (&gx)[4], const float (&gy)[4],
+                                                  const float (&gw)[4]) {
+  const long long u = (long long)it.item * pr.L + lc;
+  if constexpr (PRE == 0) {
+    if (act) {
+      float4 *gl = reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_loc) + u * 8);
+      gl[0] = make_float4(gx[0], gy[0], gx[1], gy[1]);
+      gl[1] = make_float4(gx[2], gy[2], gx[3], gy[3]);
+      *reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_attn) + u * 4) = make_float4(gw[0], gw[1], gw[2], gw[3]);
+    }
+  } else {
+    // softmax backward: S = sum over the query's L*P samples of a * d(loss)/da
+    float part = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) part += act ? a[p] * gw[p] : 0.f;
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    float ox[4], oy[4], og[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      ox[p] = __fdiv_rn(gx[p] * sc.mulx, sc.divx);
+      oy[p] = __fdiv_rn(gy[p] * sc.muly, sc.divy);
+      og[p] = a[p] * (gw[p] - part);
+    }
+    if (act) {
+      if constexpr (PRE == 1) {
+        float4 *gl = reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_loc) + u * 8);
+        gl[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);
+        gl[1] = make_float4(ox[2], oy[2], ox[3], oy[3]);
+        *reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_attn) + u * 4) = make_float4(og[0], og[1], og[2], og[3]);
+      } else if constexpr (PRE == 2) {
+        uint4 q;
+        q.x = Chan<__nv_bfloat16>::pack2(ox[0], oy[0]); q.y = Chan<__nv_bfloat16>::pack2(ox[1], oy[1]);
+        q.z = Chan<__nv_bfloat16>::pack2(ox[2], oy[2]); q.w = Chan<__nv_bfloat16>::pack2(ox[3], oy[3]);
+        *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(pr.grad_loc) + u * 8) = q;
+        *reinterpret_cast<uint2 *>(static_cast<__nv_bfloat16 *>(pr.grad_attn) + u * 4) =
+            make_uint2(Chan<__nv_bfloat16>::pack2(og[0], og[1]), Chan<__nv_bfloat16>::pack2(og[2], og[3]));
+      } else {
+        uint4 q;
+        q.x = Chan<__half>::pack2(ox[0], oy[0]); q.y = Chan<__half>::pack2(ox[1], oy[1]);
+        q.z = Chan<__half>::pack2(ox[2], oy[2]); q.w = Chan<__half>::pack2(ox[3], oy[3]);
+        *reinterpret_cast<uint4 *>(static_cast<__half *>(pr.grad_loc) + u * 8) = q;
+        *reinterpret_cast<uint2 *>(static_cast<__half *>(pr.grad_attn) + u * 4) =
+            make_uint2(Chan<__half>::pack2(og[0], og[1]), Chan<__half>::pack2(og[2], og[3]));
+      }
+    }
+  }
+}
+
 // Geometry of one sample as phase A needs it.
 struct Sample {
   float lh, lw, aw;   // fractions and attention weight, zeroed when the sample is rejected (cuh:288)
@@ -139,8 +192,13 @@ __device__ __forceinline__ Sample make_sample(float x, float y, float a, bool ac
 template <typename VT>
 struct TileFwdCfg {
   static constexpr bool wide = sizeof(typename Chan<VT>::Raw) != 16;
+#if defined(MSDA_TILE_MINB16) && defined(MSDA_TILE_RB)     // A/B builds only (MSDA_NVCC_EXTRA)
+  static constexpr int minb = wide ? 3 : MSDA_TILE_MINB16;
+  static constexpr int rb = wide ? 4 : MSDA_TILE_RB;
+#else
   static constexpr int minb = wide ? 3 : 4;      // resident CTAs per SM the kernel is register-limited for
   static constexpr int rb = 4;                   // row gathers kept in flight per lane
+#endif
 };
 template <typename VT, int MINB>
 struct RowBatch {   // backward: row gathers kept in flight per lane in the direct path (registers: 4 or 8 per gather)
@@ -651,55 +709,200 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr)
         gy[p] = (float)H * aw * (hw * (d3 - d1) + lw * (d4 - d2));
         gw[p] = hh * hw * d1 + hh * lw * d2 + lh * hw * d3 + lh * lw * d4;
       }
-      const long long u = (long long)it.item * pr.L + lc;
-      if constexpr (PRE == 0) {
-        if (act) {
-          float4 *gl = reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_loc) + u * 8);
-          gl[0] = make_float4(gx[0], gy[0], gx[1], gy[1]);
-          gl[1] = make_float4(gx[2], gy[2], gx[3], gy[3]);
-          *reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_attn) + u * 4) = make_float4(gw[0], gw[1], gw[2], gw[3]);
-        }
-      } else {
-        // softmax backward: S = sum over the query's L*P samples of a * d(loss)/da
-        float part = 0.f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) part += act ? a[p] * gw[p] : 0.f;
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        float ox[4], oy[4], og[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          ox[p] = __fdiv_rn(gx[p] * sc.mulx, sc.divx);
-          oy[p] = __fdiv_rn(gy[p] * sc.muly, sc.divy);
-          og[p] = a[p] * (gw[p] - part);
-        }
-        if (act) {
-          if constexpr (PRE == 1) {
-            float4 *gl = reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_loc) + u * 8);
-            gl[0] = make_float4(ox[0], oy[0], ox[1], oy[1]);
-            gl[1] = make_float4(ox[2], oy[2], ox[3], oy[3]);
-            *reinterpret_cast<float4 *>(static_cast<float *>(pr.grad_attn) + u * 4) = make_float4(og[0], og[1], og[2], og[3]);
-          } else if constexpr (PRE == 2) {
-            uint4 q;
-            q.x = Chan<__nv_bfloat16>::pack2(ox[0], oy[0]); q.y = Chan<__nv_bfloat16>::pack2(ox[1], oy[1]);
-            q.z = Chan<__nv_bfloat16>::pack2(ox[2], oy[2]); q.w = Chan<__nv_bfloat16>::pack2(ox[3], oy[3]);
-            *reinterpret_cast<uint4 *>(static_cast<__nv_bfloat16 *>(pr.grad_loc) + u * 8) = q;
-            *reinterpret_cast<uint2 *>(static_cast<__nv_bfloat16 *>(pr.grad_attn) + u * 4) =
-                make_uint2(Chan<__nv_bfloat16>::pack2(og[0], og[1]), Chan<__nv_bfloat16>::pack2(og[2], og[3]));
-          } else {
-            uint4 q;
-            q.x = Chan<__half>::pack2(ox[0], oy[0]); q.y = Chan<__half>::pack2(ox[1], oy[1]);
-            q.z = Chan<__half>::pack2(ox[2], oy[2]); q.w = Chan<__half>::pack2(ox[3], oy[3]);
-            *reinterpret_cast<uint4 *>(static_cast<__half *>(pr.grad_loc) + u * 8) = q;
-            *reinterpret_cast<uint2 *>(static_cast<__half *>(pr.grad_attn) + u * 4) =
-                make_uint2(Chan<__half>::pack2(og[0], og[1]), Chan<__half>::pack2(og[2], og[3]));
-          }
-        }
-      }
+      store_small_grads<PRE>(pr, it, lc, act, a, sc, gx, gy, gw);
     }
     // The next unit's step A may start at once: everything it overwrites (coef, tmp, row counters, go32, the other
     // direct-sample queue) was last read before the barrier above, except tmp, which this thread has just consumed
     // itself -- but other threads' step C still reads THEIR tmp words, which step A of a faster thread never touches.
+  }
+}
+
+// ================================================================================================ backward, warp-scoped
+// The row-group backward (msda_bwd.cu) restructured like the tile forward, WITHOUT aggregation across queries: per (query,
+// level) the scalar work -- cell, neighbour mask, bilinear coefficients, the sliding-window merge of neighbour rows shared
+// by consecutive points -- is done once by one thread (phase A) instead of four times by the lanes of a row group, and the
+// row loop reads lists from shared memory:
+//   A  thread = (query, level): 16 gather offsets (4 points x 4 neighbours, -1 = no row), a COMPACTED list of the
+//      (row offset, coefficient) reductions the window merge emits (at most 16), and the count.
+//   1  lane group = (query, level), two queries per warp pass: 16 row gathers x <grad_out, row> -> reduce-scatter over the
+//      4 lanes -> the 16 dot products overwrite the gather offsets; then the reductions: the two groups of a level pair
+//      walk BOTH lists, the first sending channels [8j, 8j+4) and the second [8j+4, 8j+8) of every row, so each
+//      red.global.add.v4.f32 instruction still covers whole 128-byte rows (as COOP in msda_bwd.cu, without the shuffles).
+//   C  thread = (query, level): grad_sampling_loc / grad_attn_weight from the dot products, 16-byte stores.
+// A warp reads only what its own 32 threads wrote: no block barrier inside the unit loop.
+constexpr int kGlStride = 20;   // ints per (query, level): 16 offsets / dot products, the count, pad.  16-byte aligned and
+                                // 20 * seg mod 32 is a permutation of the 4-word bank groups over 8 segments: LDS.128 conflict-free
+constexpr size_t kWbOffGl = kTablesBytes;
+constexpr size_t kWbOffRl = kWbOffGl + (size_t)kThreads * kGlStride * 4;
+constexpr size_t kWbOffItab = kWbOffRl + (size_t)kRecs * sizeof(int2);
+constexpr size_t kWbSmem = kWbOffItab + 256;
+
+template <typename VT, int PRE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) bwd_warp_kernel(const Problem pr) {
+  pdl_wait();
+  constexpr int D = 32, CH = 8, NP = 4;
+  static_assert(Chan<VT>::kPerLane == CH && Chan<VT>::kPairs == NP, "8 channels per lane");
+  extern __shared__ __align__(16) unsigned char smem[];
+  Tables &tb = *reinterpret_cast<Tables *>(smem);
+  int *GL = reinterpret_cast<int *>(smem + kWbOffGl);
+  int2 *RL = reinterpret_cast<int2 *>(smem + kWbOffRl);
+  int *itab = reinterpret_cast<int *>(smem + kWbOffItab);
+  load_tables(pr, tb, kTileItems);
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const VT *__restrict__ value = static_cast<const VT *>(pr.value);
+  const VT *__restrict__ grad_out = static_cast<const VT *>(pr.grad_out);
+  float *__restrict__ gacc = static_cast<float *>(pr.grad_value_acc);
+  const int MD = pr.M * D;
+
+  for (int unit = blockIdx.x; unit < tb.n_units; unit += gridDim.x) {
+    const UnitCtx uc = decode_unit(pr, tb, unit);
+    // ---- phase A: thread = (query k, level l)
+    const int k = t >> 2, l = t & 3;
+    const Item it = decode_item(pr, tb, uc, k);
+    const bool act = it.valid && l < pr.L;
+    const int lc = act ? l : 0;
+    const int H = tb.H[lc], W = tb.W[lc];
+    float xy[8], a[4];
+    OffsetScale sc;
+    thread_level_inputs<PRE>(pr, it, lc, act, H, W, xy, a, sc);
+    float g_lh[4], g_lw[4], g_aw[4];
+    {
+      const int rowbase = it.b * pr.S + tb.start[lc];
+      const int WMD = W * MD;
+      const int base_off = rowbase * MD + it.m * D;      // element offset of (first row of the level, head m)
+      int *gl = GL + t * kGlStride;
+      int2 *rl = RL + t * kRecStride;
+      if (l == 0) itab[k] = it.valid ? it.item : -1;
+      int nred = 0;
+      // sliding 2x2 window over the points of this (query, level): see msda_bwd.cu (WIN)
+      float win_c[4] = {0.f, 0.f, 0.f, 0.f};
+      int win_h = 0, win_w = 0, win_off = 0;
+      bool win_valid = false;
+      auto emit = [&](const float (&e)[4], int off) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          if (e[kk] != 0.f) {
+            rl[nred] = make_int2(off + ((kk & 1) ? MD : 0) + ((kk & 2) ? WMD : 0), __float_as_int(e[kk]));
+            ++nred;
+          }
+      };
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const Cell<float> c = locate(xy[2 * p], xy[2 * p + 1], H, W);
+        const bool in = act && c.inside;
+        int mask = in ? corner_mask(c.h_low, c.w_low, H, W) : 0;
+        if (pr.pad_mask != nullptr && mask != 0) mask = drop_padded(pr.pad_mask, mask, rowbase + c.h_low * W + c.w_low, W);
+        g_lh[p] = in ? c.lh : 0.f;
+        g_lw[p] = in ? c.lw : 0.f;
+        g_aw[p] = in ? a[p] : 0.f;
+        const float hh = 1.f - g_lh[p], hw = 1.f - g_lw[p];
+        const float ah = hh * g_aw[p], al = g_lh[p] * g_aw[p];
+        const float ncw[4] = {(mask & 1) ? ah * hw : 0.f, (mask & 2) ? ah * g_lw[p] : 0.f, (mask & 4) ? al * hw : 0.f,
+                              (mask & 8) ? al * g_lw[p] : 0.f};
+        const int o00 = in ? base_off + c.h_low * WMD + c.w_low * MD : 0;
+        *reinterpret_cast<int4 *>(gl + 4 * p) = make_int4((mask & 1) ? o00 : -1, (mask & 2) ? o00 + MD : -1,
+                                                          (mask & 4) ? o00 + WMD : -1, (mask & 8) ? o00 + WMD + MD : -1);
+        const int dh = c.h_low - win_h, dw = c.w_low - win_w;
+        const bool near = in && win_valid && (unsigned)(dh + 1) <= 2u && (unsigned)(dw + 1) <= 2u;
+        float carry[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p > 0) {
+          const float t0 = dh == 0 ? win_c[0] : (dh == 1 ? win_c[2] : 0.f);
+          const float t1 = dh == 0 ? win_c[1] : (dh == 1 ? win_c[3] : 0.f);
+          const float t2 = dh == 0 ? win_c[2] : (dh == -1 ? win_c[0] : 0.f);
+          const float t3 = dh == 0 ? win_c[3] : (dh == -1 ? win_c[1] : 0.f);
+          if (near) {
+            carry[0] = dw == 0 ? t0 : (dw == 1 ? t1 : 0.f);
+            carry[1] = dw == 0 ? t1 : (dw == -1 ? t0 : 0.f);
+            carry[2] = dw == 0 ? t2 : (dw == 1 ? t3 : 0.f);
+            carry[3] = dw == 0 ? t3 : (dw == -1 ? t2 : 0.f);
+          }
+          const bool r0 = near && dh <= 0, r1 = near && dh >= 0, c0 = dw <= 0, c1 = dw >= 0;
+          const float e[4] = {(r0 && c0) ? 0.f : win_c[0], (r0 && c1) ? 0.f : win_c[1],
+                              (r1 && c0) ? 0.f : win_c[2], (r1 && c1) ? 0.f : win_c[3]};
+          emit(e, win_off);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) win_c[kk] = ncw[kk] + carry[kk];
+        win_h = c.h_low; win_w = c.w_low; win_valid = in; win_off = o00;
+      }
+      emit(win_c, win_off);
+      gl[16] = nred;
+    }
+    __syncwarp();
+    {  // ---- row loop: two queries per warp pass (half-warps), group = level, lane = 8 channels
+      const int half = lane >> 4, g = (lane >> 2) & 3, j = lane & 3;
+      const bool first = (g & 1) == 0;
+      const VT *vbase = as_given(value + j * CH);
+      float *gbase = as_given(gacc + j * CH + (first ? 0 : 4));
+#pragma unroll 1
+      for (int pair = 0; pair < 4; ++pair) {
+        const int kq = warp * 8 + pair * 2 + half;
+        const int seg = kq * 4 + g;
+        const int item = itab[kq];
+        unsigned long long go[NP];
+        Chan<VT>::unpack2(Chan<VT>::gather(grad_out + (long long)(item < 0 ? 0 : item) * D + j * CH, item >= 0), go);
+        int *glp = GL + seg * kGlStride;
+        float d[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int4 o4 = *reinterpret_cast<const int4 *>(glp + 4 * q);
+          const int o[4] = {o4.x, o4.y, o4.z, o4.w};
+          typename Chan<VT>::Raw raw[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) raw[kk] = Chan<VT>::gather(vbase + o[kk], o[kk] >= 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            unsigned long long v[NP];
+            Chan<VT>::unpack2(raw[kk], v);
+            unsigned long long dot2 = 0ull;
+#pragma unroll
+            for (int c = 0; c < NP; ++c) dot2 = ffma2(go[c], v[c], dot2);
+            float lo, hi;
+            unpack_f2(dot2, lo, hi);
+            d[4 * q + kk] = lo + hi;
+          }
+        }
+        reduce_scatter<16, 2>(d, j);                         // lane j: the four dot products of point j
+        __syncwarp();                                        // every lane has read the offsets the dot products replace
+        *reinterpret_cast<float4 *>(glp + 4 * j) = make_float4(d[0], d[1], d[2], d[3]);
+        // reductions of this level pair: list of the even level first, then of the odd one
+        const int segA = seg & ~1;
+        const int nA = GL[segA * kGlStride + 16], nB = GL[(segA + 1) * kGlStride + 16];
+        const int tot = nA + nB;
+        const int most = __reduce_max_sync(0xffffffffu, tot);
+        const unsigned long long gsel0 = first ? go[0] : go[2], gsel1 = first ? go[1] : go[3];
+        const int2 *la = RL + segA * kRecStride, *lb = RL + (segA + 1) * kRecStride - nA;
+#pragma unroll 2
+        for (int e = 0; e < most; ++e) {
+          if (e < tot) {
+            const int2 r = e < nA ? la[e] : lb[e];
+            const float c = __int_as_float(r.y);
+            const unsigned long long c2 = pack_f2(c, c);
+            float r0, r1, r2, r3;
+            unpack_f2(fmul2(c2, gsel0), r0, r1);
+            unpack_f2(fmul2(c2, gsel1), r2, r3);
+            red_add_f32x4(gbase + r.x, r0, r1, r2, r3);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    {  // ---- phase C: the two small gradients of my (query, level)
+      const float *dq = reinterpret_cast<const float *>(GL + t * kGlStride);
+      float gx[4], gy[4], gw[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float4 dd = *reinterpret_cast<const float4 *>(dq + 4 * p);
+        const float lh = g_lh[p], lw = g_lw[p], aw = g_aw[p];
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        gx[p] = (float)W * aw * (hh * (dd.y - dd.x) + lh * (dd.w - dd.z));
+        gy[p] = (float)H * aw * (hw * (dd.z - dd.x) + lw * (dd.w - dd.y));
+        gw[p] = hh * hw * dd.x + hh * lw * dd.y + lh * hw * dd.z + lh * lw * dd.w;
+      }
+      store_small_grads<PRE>(pr, it, lc, act, a, sc, gx, gy, gw);
+    }
+    __syncwarp();        // the next unit's phase A overwrites the warp's lists
   }
 }
 
@@ -749,6 +952,29 @@ int launch_forward_tile(const Problem &pr, int dtype, int sms, int pre, cudaStre
   if (dtype == MSDA_F32) return launch_fwd<wide_f32>(pr, sms, pre, stream);
   if (dtype == MSDA_BF16) return launch_fwd<__nv_bfloat16>(pr, sms, pre, stream);
   if (dtype == MSDA_F16) return launch_fwd<__half>(pr, sms, pre, stream);
+  return MSDA_E_UNSUPPORTED;
+}
+
+#ifndef MSDA_WARP_BWD_MINB
+#define MSDA_WARP_BWD_MINB 3
+#endif
+template <typename VT>
+int launch_bwd_warp(const Problem &pr, int sms, int pre, cudaStream_t stream) {
+  constexpr int MB = MSDA_WARP_BWD_MINB;
+#define MSDA_WARP_BWD(PREV)                                                              \
+  if (pre == PREV) {                                                                     \
+    if (int rc = set_smem(bwd_warp_kernel<VT, PREV, MB>, kWbSmem)) return rc;            \
+    return launch_pdl(bwd_warp_kernel<VT, PREV, MB>, sms * MB, kThreads, kWbSmem, stream, pr);  \
+  }
+  MSDA_WARP_BWD(0) MSDA_WARP_BWD(1) MSDA_WARP_BWD(2) MSDA_WARP_BWD(3)
+#undef MSDA_WARP_BWD
+  return MSDA_E_UNSUPPORTED;
+}
+
+int launch_backward_warp(const Problem &pr, int dtype, int sms, int pre, cudaStream_t stream) {
+  if (dtype == MSDA_F32) return launch_bwd_warp<wide_f32>(pr, sms, pre, stream);
+  if (dtype == MSDA_BF16) return launch_bwd_warp<__nv_bfloat16>(pr, sms, pre, stream);
+  if (dtype == MSDA_F16) return launch_bwd_warp<__half>(pr, sms, pre, stream);
   return MSDA_E_UNSUPPORTED;
 }
 

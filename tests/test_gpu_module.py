@@ -266,7 +266,7 @@ def test_no_out_of_bounds_writes(dtype):
     ws_bytes = lib.msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, 0)
     a_ws, ws = arena(max(ws_bytes, 16), torch.uint8)
     stream = torch.cuda.current_stream().cuda_stream
-    for variant in (1, 2, 3, 3 | 0x400, 3 | 0x800):
+    for variant in (1, 2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x1000):
         _lib.check(lib.msda_forward(value.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                                     out.data_ptr(), N, S, M, D, L, Lq, P, code, variant, stream), "fwd")
         _lib.check(lib.msda_backward(value.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), attn.data_ptr(),
