@@ -79,13 +79,17 @@ const char *msda_error_string(int code);
  * bit 10     : MSDA_VARIANT_OLD_TILED -- in query-tile order use the row-group vector kernels instead of the phase-
  *             structured tile kernels (A/B measurements; both are complete implementations)
  * bit 11     : MSDA_VARIANT_TILE_BWD -- (backward, query-tile order, D = 32, P = 4, L <= 4) use the tile backward (per-tile
- *             counting sort by value row + row-stationary accumulation) instead of the default row-group kernel
+ *             counting sort by value row + row-stationary accumulation) instead of the default warp-scoped kernel
+ * bit 12     : MSDA_VARIANT_WARP_BWD -- the warp-scoped backward of the query-tile order (the default there; accepted, no effect)
+ * bit 13     : MSDA_VARIANT_ROWGROUP_BWD -- (backward, query-tile order) keep the tile forward's counterpart out and use the
+ *             row-group vector kernel of msda_bwd.cu (the default until round 2; A/B measurements, also on the fused entry points)
  * other bits: reserved, must be 0. */
 #define MSDA_VARIANT_NO_ZERO 0x100
 #define MSDA_VARIANT_NO_NARROW 0x200
 #define MSDA_VARIANT_OLD_TILED 0x400
 #define MSDA_VARIANT_TILE_BWD 0x800
 #define MSDA_VARIANT_WARP_BWD 0x1000
+#define MSDA_VARIANT_ROWGROUP_BWD 0x2000
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output,
                  int batch, int spatial_size, int num_heads, int channels, int num_levels,

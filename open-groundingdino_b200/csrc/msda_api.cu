@@ -176,13 +176,15 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     pr.tiled = (family == 3);
     pr.win_margin = window_margin();
     const int abl = (variant >> 6) & 3;   // profiling ablations, see msda_bwd.cu
-    // The tile backward (counting sort + row-stationary pass, msda_tile.cu) is correct and sends 3x fewer reductions to
-    // the L2, but measured slower than the row-group kernel (0.93 vs 0.75 ms at cfg-2, profiles/r02_tile_backward.md):
-    // opt-in through MSDA_VARIANT_TILE_BWD.
-    if ((variant & MSDA_VARIANT_WARP_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
-      rc = launch_backward_warp(pr, dtype, sm_count(), 0, stream);
-    else if ((variant & MSDA_VARIANT_TILE_BWD) && use_tile_kernels(variant, family, dtype, pr) && !abl)
+    // Query-tile order, D = 32, P = 4, L <= 4: the warp-scoped backward of msda_tile.cu (0.68 ms at cfg-2 against 0.73 ms
+    // for the row-group kernel, which MSDA_VARIANT_ROWGROUP_BWD selects).  The tile backward with aggregation across
+    // queries (counting sort + row-stationary pass) is correct and sends 3x fewer reductions to the L2, but measured slower
+    // (0.93 ms, profiles/r02_tile_backward.md): opt-in through MSDA_VARIANT_TILE_BWD.
+    const bool tile_ok = use_tile_kernels(variant, family, dtype, pr) && !abl;
+    if (tile_ok && (variant & MSDA_VARIANT_TILE_BWD))
       rc = launch_backward_tile(pr, dtype, sm_count(), 0, stream);
+    else if (tile_ok && !(variant & MSDA_VARIANT_ROWGROUP_BWD))
+      rc = launch_backward_warp(pr, dtype, sm_count(), 0, stream);
     else rc = launch_backward_vec(pr, dtype, vec_grid(pr, min_blocks(variant, 2)), abl ? 100 + abl : min_blocks(variant, 2), stream);
   }
   if (rc != MSDA_OK) return rc;
@@ -280,7 +282,10 @@ int msda_fused_backward_masked(const void *value, const unsigned char *padding_m
   if (cudaError_t e = cudaMemsetAsync(acc, 0, n_value * 4, stream)) return (int)e;
   const int pre = q_dtype == MSDA_BF16 ? 2 : q_dtype == MSDA_F16 ? 3 : 1;
   pr.win_margin = window_margin();
-  int rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), 200 + pre, stream);
+  int rc;
+  if (use_tile_kernels(variant, pr.tiled ? 3 : 2, dtype, pr) && !(variant & MSDA_VARIANT_ROWGROUP_BWD))
+    rc = launch_backward_warp(pr, dtype, sm_count(), pre, stream);
+  else rc = launch_backward_vec(pr, dtype, vec_grid(pr, 2), 200 + pre, stream);
   if (rc != MSDA_OK) return rc;
   if (is16(dtype))
     rc = launch_f32_to_bf16(static_cast<const float *>(acc), grad_value, (long long)n_value, D, pr.acc_permuted != 0,

@@ -718,6 +718,9 @@ __global__ void __launch_bounds__(kThreads, 2) bwd_tile_kernel(const Problem pr)
 }
 
 // ================================================================================================ backward, warp-scoped
+#ifndef MSDA_WARP_BWD_QB
+#define MSDA_WARP_BWD_QB 2
+#endif
 // The row-group backward (msda_bwd.cu) restructured like the tile forward, WITHOUT aggregation across queries: per (query,
 // level) the scalar work -- cell, neighbour mask, bilinear coefficients, the sliding-window merge of neighbour rows shared
 // by consecutive points -- is done once by one thread (phase A) instead of four times by the lanes of a row group, and the
@@ -741,6 +744,7 @@ template <typename VT, int PRE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) bwd_warp_kernel(const Problem pr) {
   pdl_wait();
   constexpr int D = 32, CH = 8, NP = 4;
+  constexpr int QB = MSDA_WARP_BWD_QB;
   static_assert(Chan<VT>::kPerLane == CH && Chan<VT>::kPairs == NP, "8 channels per lane");
   extern __shared__ __align__(16) unsigned char smem[];
   Tables &tb = *reinterpret_cast<Tables *>(smem);
@@ -845,22 +849,25 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_warp_kernel(const Problem 
         int *glp = GL + seg * kGlStride;
         float d[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int4 o4 = *reinterpret_cast<const int4 *>(glp + 4 * q);
-          const int o[4] = {o4.x, o4.y, o4.z, o4.w};
-          typename Chan<VT>::Raw raw[4];
+        for (int q0 = 0; q0 < 4; q0 += QB) {                 // QB points = 4 * QB row gathers in flight per lane
+          typename Chan<VT>::Raw raw[4 * QB];
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) raw[kk] = Chan<VT>::gather(vbase + o[kk], o[kk] >= 0);
+          for (int q = 0; q < QB; ++q) {
+            const int4 o4 = *reinterpret_cast<const int4 *>(glp + 4 * (q0 + q));
+            const int o[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) raw[4 * q + kk] = Chan<VT>::gather(vbase + o[kk], o[kk] >= 0);
+          }
+#pragma unroll
+          for (int i = 0; i < 4 * QB; ++i) {
             unsigned long long v[NP];
-            Chan<VT>::unpack2(raw[kk], v);
+            Chan<VT>::unpack2(raw[i], v);
             unsigned long long dot2 = 0ull;
 #pragma unroll
             for (int c = 0; c < NP; ++c) dot2 = ffma2(go[c], v[c], dot2);
             float lo, hi;
             unpack_f2(dot2, lo, hi);
-            d[4 * q + kk] = lo + hi;
+            d[4 * q0 + i] = lo + hi;
           }
         }
         reduce_scatter<16, 2>(d, j);                         // lane j: the four dot products of point j
@@ -869,22 +876,29 @@ __global__ void __launch_bounds__(kThreads, MINB) bwd_warp_kernel(const Problem 
         // reductions of this level pair: list of the even level first, then of the odd one
         const int segA = seg & ~1;
         const int nA = GL[segA * kGlStride + 16], nB = GL[(segA + 1) * kGlStride + 16];
-        const int tot = nA + nB;
-        const int most = __reduce_max_sync(0xffffffffu, tot);
         const unsigned long long gsel0 = first ? go[0] : go[2], gsel1 = first ? go[1] : go[3];
-        const int2 *la = RL + segA * kRecStride, *lb = RL + (segA + 1) * kRecStride - nA;
-#pragma unroll 2
-        for (int e = 0; e < most; ++e) {
-          if (e < tot) {
-            const int2 r = e < nA ? la[e] : lb[e];
-            const float c = __int_as_float(r.y);
-            const unsigned long long c2 = pack_f2(c, c);
-            float r0, r1, r2, r3;
-            unpack_f2(fmul2(c2, gsel0), r0, r1);
-            unpack_f2(fmul2(c2, gsel1), r2, r3);
-            red_add_f32x4(gbase + r.x, r0, r1, r2, r3);
+        auto send = [&](const int2 &r) {
+          const float c = __int_as_float(r.y);
+          const unsigned long long c2 = pack_f2(c, c);
+          float r0, r1, r2, r3;
+          unpack_f2(fmul2(c2, gsel0), r0, r1);
+          unpack_f2(fmul2(c2, gsel1), r2, r3);
+          red_add_f32x4(gbase + r.x, r0, r1, r2, r3);
+        };
+        auto walk = [&](const int2 *list, int n) {          // every entry of a list has a non-zero coefficient
+          const int most = __reduce_max_sync(0xffffffffu, n);
+#pragma unroll 1
+          for (int e = 0; e < most; e += 2) {
+            const bool p0 = e < n, p1 = e + 1 < n;
+            int2 e0 = make_int2(0, 0), e1 = make_int2(0, 0);
+            if (p0) e0 = list[e];
+            if (p1) e1 = list[e + 1];
+            if (p0) send(e0);
+            if (p1) send(e1);
           }
-        }
+        };
+        walk(RL + segA * kRecStride, nA);
+        walk(RL + (segA + 1) * kRecStride, nB);
       }
     }
     __syncwarp();

@@ -152,6 +152,10 @@ class MSDeformAttnFunction(Function):
 
 
 # ---- fused pre-op ----------------------------------------------------------
+# variant bits handed to the fused entry points (include/msda_b200.h); tests set it to reach the alternative kernels
+fused_variant = 0
+
+
 def fused_supported(value, sampling_offsets, attn_logits, reference_points, n_levels, n_points) -> bool:
     """True when libmsda_b200 can take the raw offsets / logits directly (see include/msda_b200.h)."""
     if not (value.is_cuda and value.dtype in (torch.float32, torch.bfloat16, torch.float16)):
@@ -217,7 +221,7 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
         rc = _lib.lib().msda_fused_forward_masked(
             value.data_ptr(), mask_ptr, spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
             attention_logits.data_ptr(), reference_points.data_ptr(), output.data_ptr(), N, S, M, D, L, Lq, P,
-            reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], 0,
+            reference_points.shape[-1], _DTYPE_CODE[value.dtype], _DTYPE_CODE[sampling_offsets.dtype], fused_variant,
             torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "msda_fused_forward")
     return output
@@ -243,7 +247,7 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
             value.data_ptr(), mask_ptr, spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_offsets.data_ptr(),
             attention_logits.data_ptr(), reference_points.data_ptr(), grad_output.data_ptr(), grad_value.data_ptr(),
             grad_offsets.data_ptr(), grad_logits.data_ptr(), N, S, M, D, L, Lq, P, reference_points.shape[-1], code,
-            _DTYPE_CODE[sampling_offsets.dtype], 0, workspace.data_ptr() if workspace is not None else None, ws_bytes,
+            _DTYPE_CODE[sampling_offsets.dtype], fused_variant, workspace.data_ptr() if workspace is not None else None, ws_bytes,
             torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "msda_fused_backward")
     return grad_value, grad_offsets, grad_logits

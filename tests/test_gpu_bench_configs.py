@@ -117,12 +117,12 @@ def test_cfg3_decoder_bs8(dtype, tol, small):
         _check(g, dtype, tol, small)
 
 
-@pytest.mark.parametrize("variant", [3 | 0x800, 3 | 0x1000])
+@pytest.mark.parametrize("variant", [3 | 0x800, 3 | 0x2000])
 @pytest.mark.parametrize("dist", ["I", "U"])
 def test_cfg2_tile_backward_bf16_bs4(dist, variant):
     """The alternative backward kernels of the query-tile order at the headline size -- MSDA_VARIANT_TILE_BWD (counting sort +
     row-stationary pass: every window level, directly handled samples (U: nearly all of them) and the sort capacity limits
-    are exercised only at full size) and MSDA_VARIANT_WARP_BWD (warp-scoped lists)."""
+    are exercised only at full size) and MSDA_VARIANT_ROWGROUP_BWD (the row-group kernel; the default is the warp-scoped one)."""
     g = _round_inputs(make_inputs(SWIN_T_800x1333, N=4, M=8, D=32, Lq=None, P=4, dist=dist, seed=59), torch.bfloat16)
     res = _ours(g, torch.bfloat16, variant=variant)
     theirs = _reference_op_wrapped(g, torch.bfloat16)

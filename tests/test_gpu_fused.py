@@ -29,8 +29,13 @@ def _unfused(value, sh, st, off, logit, ref, P):
 @pytest.mark.parametrize("vdt,qdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16),
                                      (torch.float16, torch.float16), (torch.float16, torch.float32)])
 @pytest.mark.parametrize("encoder", [True, False])
-def test_fused_function_matches_unfused(ref_dim, vdt, qdt, encoder):
+@pytest.mark.parametrize("fused_variant", [0, 0x2000, 0x400])   # default kernels / row-group backward / row-group both ways
+def test_fused_function_matches_unfused(ref_dim, vdt, qdt, encoder, fused_variant, monkeypatch):
+    from msda_b200 import functions
     from msda_b200.functions import MSDeformAttnFusedFunction, fused_supported
+    if fused_variant and not encoder:
+        pytest.skip("the variants only differ in query-tile order (encoder shapes)")
+    monkeypatch.setattr(functions, "fused_variant", fused_variant)
     torch.manual_seed(ref_dim * 7 + (vdt == torch.bfloat16) + 2 * (qdt == torch.bfloat16) + 4 * (vdt == torch.float16))
     sh, st = _tables(SHAPES)
     S = int(sh.prod(1).sum())

@@ -84,11 +84,16 @@ def test_module_matches_reference_math(ref_dim, autocast):
 
 @pytest.mark.parametrize("encoder", [True, False])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
-def test_padding_mask_in_kernel_equals_masked_fill(dtype, encoder):
+@pytest.mark.parametrize("fused_variant", [0, 0x2000])          # encoder: warp-scoped backward (default) / row-group backward
+def test_padding_mask_in_kernel_equals_masked_fill(dtype, encoder, fused_variant, monkeypatch):
     """Scope row f4: the fused kernels take input_padding_mask themselves (padded rows gather as zero, zero grad_value rows)
     and the module skips value.masked_fill (ops/modules/ms_deform_attn.py:95-96).  Same results as the masked_fill path, in
     query-tile order (encoder) and linear order (decoder), and grad_value of the padded rows is exactly zero."""
+    from msda_b200 import functions
     from msda_b200.functions import MSDeformAttnFusedFunction
+    if fused_variant and not encoder:
+        pytest.skip("the variants only differ in query-tile order")
+    monkeypatch.setattr(functions, "fused_variant", fused_variant)
     torch.manual_seed(17 + encoder)
     sh, st = _tables(SHAPES)
     S = int(sh.prod(1).sum())
@@ -266,7 +271,7 @@ def test_no_out_of_bounds_writes(dtype):
     ws_bytes = lib.msda_backward_workspace_bytes(N, S, M, D, L, Lq, P, code, 0)
     a_ws, ws = arena(max(ws_bytes, 16), torch.uint8)
     stream = torch.cuda.current_stream().cuda_stream
-    for variant in (1, 2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x1000):
+    for variant in (1, 2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x2000):
         _lib.check(lib.msda_forward(value.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), attn.data_ptr(),
                                     out.data_ptr(), N, S, M, D, L, Lq, P, code, variant, stream), "fwd")
         _lib.check(lib.msda_backward(value.data_ptr(), sh.data_ptr(), st.data_ptr(), loc.data_ptr(), attn.data_ptr(),

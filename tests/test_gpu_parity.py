@@ -24,7 +24,7 @@ BF16_TOL = 1e-2
 # P = 4, L <= 4), backward on the row-group vector kernel; rowgroup_tiled forces the row-group forward as well
 # (MSDA_VARIANT_OLD_TILED); tile_bwd opts into the tile backward (MSDA_VARIANT_TILE_BWD: counting sort + row-stationary pass)
 FAMILIES = {"generic": 1, "vec_linear": 2, "vec_tiled": 3, "rowgroup_tiled": 3 | 0x400, "tile_bwd": 3 | 0x800,
-            "warp_bwd": 3 | 0x1000}
+            "rowgroup_bwd": 3 | 0x2000}
 
 
 def dev(a, dtype=None):
@@ -84,7 +84,7 @@ def test_reference_testpy_acceptance():
     assert np.allclose(out32, g["out_f32"], rtol=1e-2, atol=1e-3)
 
 
-@pytest.mark.parametrize("family", ["generic", "vec_linear", "vec_tiled", "rowgroup_tiled", "tile_bwd", "warp_bwd"])
+@pytest.mark.parametrize("family", ["generic", "vec_linear", "vec_tiled", "rowgroup_tiled", "tile_bwd", "rowgroup_bwd"])
 @pytest.mark.parametrize("name", ["pyr4_bf16_D32", "pyr4_wide_D32", "pyr5_P8_D16"])
 def test_golden_bf16_value(name, family):
     g = dict(load_golden(name))
@@ -313,7 +313,7 @@ def test_window_aggregation_chains(kind, dtype):
         tol = BF16_TOL
     truth_out = oracle.forward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], np.float64)
     truth = (truth_out,) + oracle.backward(g["value"], g["shapes"], g["starts"], g["loc"], g["attn"], g["grad_out"], np.float64)
-    for code in (2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x1000):
+    for code in (2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x2000):
         check_all(g, run_cuda(g, dtype, code), truth, tol)
 
 
@@ -374,5 +374,5 @@ def test_tile_kernels_level_and_head_counts(dtype, L, M):
         g["value"] = rnd(g["value"]); g["grad_out"] = rnd(g["grad_out"])
         args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
         truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
-        for code in (3, 3 | 0x800, 3 | 0x1000):
+        for code in (3, 3 | 0x800, 3 | 0x2000):
             check_all(g, run_cuda(g, dtype, code), truth, tol)

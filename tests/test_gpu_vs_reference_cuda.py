@@ -35,7 +35,7 @@ def both(g, variant=0):
 
 
 @pytest.mark.parametrize("dist", ["U", "W", "I"])
-@pytest.mark.parametrize("variant", [1, 2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x1000])
+@pytest.mark.parametrize("variant", [1, 2, 3, 3 | 0x400, 3 | 0x800, 3 | 0x2000])
 def test_matches_reference_cuda_full_size(dist, variant):
     g = make_inputs(SWIN_T_800x1333, N=1, M=8, D=32, Lq=None, P=4, dist=dist, seed=31)
     ours, theirs = both(g, variant)
