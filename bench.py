@@ -402,7 +402,10 @@ def run_ours(args, cfg):
             traffic = json.load(open(tpath)).get(args.config)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "bwd_vec_kernel (grad_value scatter + grad_loc/grad_attn)",
+    # encoder shapes (one query per pixel, D = 32, P = 4, L <= 4) run the warp-scoped backward of msda_tile.cu, the rest the
+    # row-group kernel of msda_bwd.cu (csrc/msda_api.cu)
+    bwd_name = "bwd_warp_kernel" if (Lq == S and L <= 4 and cfg.get("D", 32) == 32 and cfg.get("P", 4) == 4) else "bwd_vec_kernel"
+    roofline = {"bound": "hbm", "kernel": bwd_name + " (grad_value scatter + grad_loc/grad_attn)",
                 "achieved": bwd_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bwd_gbs / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": b_bwd, "kernel_ms": bwd_kernel_ms,
                 "fwd_kernel": {"achieved": b_fwd / (fwd_kernel_ms * 1e-3) / 1e9, "kernel_ms": fwd_kernel_ms,
