@@ -25,6 +25,10 @@
 //      per instruction (group pairs cooperate as in msda_bwd.cu).
 //   C  (backward) grad_sampling_loc / grad_attn_weight, one thread per (query, level), plain 16-byte stores.
 //
+// Three kernels live here: fwd_tile_kernel (phases A + 1, the default forward of these shapes), bwd_warp_kernel (the default
+// backward: phases A + 1 + C at warp scope, per-query reduction lists instead of phase 2, see its own header below) and
+// bwd_tile_kernel (all four phases with the per-tile aggregation of phase 2; opt-in, measured slower).
+//
 // The window placement assumes what encoder self-attention does -- query i is pixel i of its level and samples near
 // its own position on every level (models/GroundingDINO/transformer.py:470-485) -- but only performance depends on it.
 #include "msda_common.cuh"
