@@ -80,7 +80,8 @@ const char *msda_error_string(int code);
  *             structured tile kernels (A/B measurements; both are complete implementations)
  * bit 11     : MSDA_VARIANT_TILE_BWD -- (backward, query-tile order, D = 32, P = 4, L <= 4) use the tile backward (per-tile
  *             counting sort by value row + row-stationary accumulation) instead of the default warp-scoped kernel
- * bit 12     : MSDA_VARIANT_WARP_BWD -- the warp-scoped backward of the query-tile order (the default there; accepted, no effect)
+ * bit 12     : MSDA_VARIANT_FORCE_TILE -- use the tile kernels also with 1 or 2 levels, where the dispatcher prefers the
+ *             row-group kernels (tests)
  * bit 13     : MSDA_VARIANT_ROWGROUP_BWD -- (backward, query-tile order) keep the tile forward's counterpart out and use the
  *             row-group vector kernel of msda_bwd.cu (the default until round 2; A/B measurements, also on the fused entry points)
  * other bits: reserved, must be 0. */
@@ -88,7 +89,7 @@ const char *msda_error_string(int code);
 #define MSDA_VARIANT_NO_NARROW 0x200
 #define MSDA_VARIANT_OLD_TILED 0x400
 #define MSDA_VARIANT_TILE_BWD 0x800
-#define MSDA_VARIANT_WARP_BWD 0x1000
+#define MSDA_VARIANT_FORCE_TILE 0x1000
 #define MSDA_VARIANT_ROWGROUP_BWD 0x2000
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output,

@@ -64,6 +64,10 @@ int min_blocks(int variant, int dflt) {
 // query-tile order (family 3) runs on the tile kernels of msda_tile.cu where they exist; MSDA_VARIANT_OLD_TILED keeps the
 // round-1 vector kernels in that order (A/B measurements)
 bool use_tile_kernels(int variant, int family, int dtype, const Problem &pr) {
+  // With one or two levels half or more of the tile kernels' (query, level) threads and lane groups idle and the row-group
+  // kernels are faster (forward 0.130 vs 0.188 ms at L = 1, 0.247 vs 0.277 ms at L = 2, bs 4 fp32; profiles/r02_shape_sweep.md):
+  // there the tile kernels run only when MSDA_VARIANT_FORCE_TILE asks for them.
+  if (pr.L < 3 && !(variant & MSDA_VARIANT_FORCE_TILE)) return false;
   return family == 3 && !(variant & MSDA_VARIANT_OLD_TILED) && tile_supported(dtype, pr.N, pr.S, pr.M, pr.D, pr.L, pr.P);
 }
 

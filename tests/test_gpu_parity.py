@@ -374,5 +374,6 @@ def test_tile_kernels_level_and_head_counts(dtype, L, M):
         g["value"] = rnd(g["value"]); g["grad_out"] = rnd(g["grad_out"])
         args = (g["value"], g["shapes"], g["starts"], g["loc"], g["attn"])
         truth = (oracle.forward(*args, np.float64),) + oracle.backward(*args, g["grad_out"], np.float64)
-        for code in (3, 3 | 0x800, 3 | 0x2000):
+        # 0x1000 (MSDA_VARIANT_FORCE_TILE): with 1 or 2 levels the dispatcher would otherwise pick the row-group kernels
+        for code in (3, 3 | 0x1000, 3 | 0x1800, 3 | 0x2000):
             check_all(g, run_cuda(g, dtype, code), truth, tol)

@@ -8,6 +8,7 @@ import numpy as np, torch
 from msda_b200 import functions as F
 
 PYRAMID = [(100, 167), (50, 84), (25, 42), (13, 21), (7, 11)]
+VARIANT = int(os.environ.get("MSDA_SWEEP_VARIANT", "0"), 0)      # include/msda_b200.h variant bits, for A/B runs
 
 def case(L, P, M, N, dtype, mode, iters=5, sets=3):
     D = 256 // M
@@ -29,8 +30,8 @@ def case(L, P, M, N, dtype, mode, iters=5, sets=3):
     for it in range(iters + 1):
         for v, loc, aw, go in bufs:
             a, b, c = ev(), ev(), ev()
-            a.record(); F.ms_deform_attn_forward(v, sh, st, loc, aw, 64); b.record()
-            F.ms_deform_attn_backward(v, sh, st, loc, aw, go, 64, mode=mode); c.record()
+            a.record(); F.ms_deform_attn_forward(v, sh, st, loc, aw, 64, variant=VARIANT); b.record()
+            F.ms_deform_attn_backward(v, sh, st, loc, aw, go, 64, mode=mode, variant=VARIANT); c.record()
             torch.cuda.synchronize()
             if it:
                 tf.append(a.elapsed_time(b)); tb.append(b.elapsed_time(c))
@@ -46,7 +47,7 @@ if __name__ == "__main__":
     print("|---|---|---|---|---|---|---|---|---|---|")
     cases = []
     for L in (1, 2, 3, 4, 5):
-        cases.append((L, 4, 8, 4, torch.float32, 0))
+        cases += [(L, 4, 8, 4, torch.float32, 0), (L, 4, 8, 4, torch.bfloat16, 0)]
     for P in (8,):
         cases += [(4, P, 8, 4, torch.float32, 0), (4, P, 8, 4, torch.bfloat16, 0)]
     for M in (16,):
@@ -54,7 +55,7 @@ if __name__ == "__main__":
     for N in (1, 2, 4, 8, 16, 32):
         cases += [(4, 4, 8, N, torch.float32, 0), (4, 4, 8, N, torch.bfloat16, 0)]
     cases += [(4, 4, 8, 4, torch.float32, 1), (4, 4, 8, 4, torch.bfloat16, 1)]
-    if a.quick: cases = cases[:4]
+    if a.quick: cases = cases[:6]
     for L, P, M, N, dt, mode in cases:
         f, b, gf, gb = case(L, P, M, N, dt, mode)
         print(f"| {L} | {P} | {M} x {256 // M} | {N} | {'bf16' if dt == torch.bfloat16 else 'fp32'} | {'deterministic' if mode else 'atomic'} | {f:.3f} | {b:.3f} | {gf:.0f} | {gb:.0f} |", flush=True)
